@@ -1,0 +1,335 @@
+"""fhe_regex_b200 -- B200-native TFHE evaluation backend for fhe-regex's execution hot path.
+
+Thin ctypes binding of the C ABI in include/fhe_b200.h (libfhe_b200.so: hand-written sm_100a CUDA
+kernels + C++ host).  Names follow the reference: `has_match(server_key, content, pattern)`
+(src/regex/engine.rs:8), `encrypt_str` / `gen_keys` (src/regex/ciphertext.rs:32-45), `parse`
+(src/regex/parser.rs:146).  There is no CPU fallback: compute entry points raise without a B200.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libfhe_b200.so")
+
+BIG, SMALL, POLY = 2049, 743, 2048
+KSK_WORDS = 2048 * 5 * 743
+BSK_WORDS = 742 * 2 * 2 * 2048
+
+FB_OK, FB_ERR_NO_DEVICE, FB_ERR_CUDA, FB_ERR_ARG, FB_ERR_NO_KEY, FB_ERR_PARSE, FB_ERR_PANIC, FB_ERR_FORMAT = 0, -1, -2, -3, -4, -5, -6, -7
+
+
+class FbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libfhe_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class ParseError(FbError):
+    """anyhow::Error of parse() (parser.rs:146-184)."""
+
+
+class ReferencePanic(FbError):
+    """Input on which the reference panics (engine.rs:189-190, parser.rs:349-351)."""
+
+
+class MatchStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("variants", "ct_ops", "cache_hits", "ops_eq", "ops_gt", "ops_le", "ops_and",
+                                          "ops_or", "ops_not", "pbs", "levels", "max_level_width")] + [("gpu_ms", C.c_double)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class KernelStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("ks_launches", "br_launches", "lin_launches", "ks_samples", "br_samples")] + \
+               [(n, C.c_double) for n in ("ks_ms", "br_ms", "lin_ms")]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+_lib = None
+
+
+def lib():
+    """Load libfhe_b200.so (building it first if the sources are newer).  Fails loudly if missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        from . import build as _b
+        _b.build()
+    L = C.CDLL(LIB_PATH)
+    vp, u64p, u32p, u8p = C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint8)
+    sz = C.c_size_t
+    L.fb_ctx_create.argtypes = [C.POINTER(vp), C.c_int]
+    L.fb_ctx_destroy.argtypes = [vp]
+    L.fb_ctx_destroy.restype = None
+    L.fb_last_error.argtypes = [vp]
+    L.fb_last_error.restype = C.c_char_p
+    L.fb_ctx_stream.argtypes = [vp]
+    L.fb_ctx_stream.restype = vp
+    L.fb_sync.argtypes = [vp]
+    L.fb_load_server_key_raw.argtypes = [vp, vp, vp]
+    L.fb_get_fourier_bsk.argtypes = [vp, vp]
+    L.fb_keyswitch_batch.argtypes = [vp, vp, sz, vp]
+    L.fb_pbs_batch.argtypes = [vp, vp, vp, sz, vp, sz, vp]
+    L.fb_bootstrap_small_batch.argtypes = [vp, vp, vp, sz, vp, sz, vp]
+    L.fb_pbs_batch_dev.argtypes = [vp, vp, vp, vp, sz, vp]
+    L.fb_has_match.argtypes = [vp, vp, sz, C.c_char_p, vp, C.POINTER(MatchStats)]
+    L.fb_has_match_shard.argtypes = [vp, vp, sz, C.c_char_p, C.c_int, C.c_int, vp, C.POINTER(MatchStats)]
+    L.fb_or_fold.argtypes = [vp, vp, sz, vp]
+    L.fb_parse_debug.argtypes = [C.c_char_p, C.c_char_p, sz]
+    L.fb_plan_stats.argtypes = [C.c_char_p, sz, C.POINTER(MatchStats)]
+    L.fb_plan_eval_plain.argtypes = [C.c_char_p, vp, sz, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    L.fb_kernel_stats_reset.argtypes = [vp]
+    L.fb_kernel_stats_get.argtypes = [vp, C.POINTER(KernelStats)]
+    L.fb_kernel_timing_enable.argtypes = [vp, C.c_int]
+    L.fb_client_key_from_bincode.argtypes = [vp, sz, vp, vp]
+    L.fb_client_keygen_server.argtypes = [vp, vp, C.c_uint64, vp, vp]
+    L.fb_client_encrypt_str.argtypes = [vp, vp, sz, C.c_uint64, vp]
+    L.fb_client_trivial_str.argtypes = [vp, sz, vp]
+    L.fb_client_encrypt_block.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64, vp]
+    L.fb_client_phase.argtypes = [vp, sz, vp]
+    L.fb_client_phase.restype = C.c_uint64
+    L.fb_client_decrypt_block.argtypes = [vp, vp]
+    L.fb_client_decrypt_block.restype = C.c_uint64
+    L.fb_client_decrypt_radix.argtypes = [vp, vp]
+    L.fb_client_decrypt_radix.restype = C.c_uint64
+    L.fb_make_lut.argtypes = [vp, vp]
+    _lib = L
+    return L
+
+
+def _p(a: np.ndarray):
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _raise(code, msg):
+    if code == FB_ERR_PARSE:
+        raise ParseError(code, msg)
+    if code == FB_ERR_PANIC:
+        raise ReferencePanic(code, msg)
+    raise FbError(code, msg)
+
+
+# -------------------------------------------------------------------------------------------------
+# host-only surface (no GPU needed)
+# -------------------------------------------------------------------------------------------------
+def parse(pattern: str) -> str:
+    """parse() of the reference (parser.rs:146); returns the `{:?}` rendering of the RegExpr."""
+    buf = C.create_string_buffer(1 << 16)
+    rc = lib().fb_parse_debug(pattern.encode("latin-1"), buf, len(buf))
+    if rc != FB_OK:
+        _raise(rc, buf.value.decode("latin-1"))
+    return buf.value.decode("latin-1")
+
+
+def plan_stats(pattern: str, n_chars: int) -> dict:
+    st = MatchStats()
+    rc = lib().fb_plan_stats(pattern.encode("latin-1"), n_chars, C.byref(st))
+    if rc != FB_OK:
+        _raise(rc, "plan failed for %r" % pattern)
+    return st.as_dict()
+
+
+def plan_eval_plain(pattern: str, content: str, rank: int = 0, world: int = 1) -> int:
+    """Dry run of the lowered PBS circuit on cleartext bytes (host only): the 0/1 decrypt would give."""
+    b = content.encode("latin-1")
+    raw = np.frombuffer(b, dtype=np.uint8) if len(b) else np.zeros(1, dtype=np.uint8)
+    res = C.c_int(-1)
+    rc = lib().fb_plan_eval_plain(pattern.encode("latin-1"), _p(np.ascontiguousarray(raw)), len(b), rank, world, C.byref(res))
+    if rc != FB_OK:
+        _raise(rc, "plan dry run failed for %r" % pattern)
+    return res.value
+
+
+def make_lut(f) -> np.ndarray:
+    table = np.array([int(f(i)) & 15 for i in range(16)], dtype=np.uint64)
+    out = np.empty(POLY, dtype=np.uint64)
+    lib().fb_make_lut(_p(table), _p(out))
+    return out
+
+
+class ClientKey:
+    """RadixClientKey: secret keys as serialized in test_data/client_key (engine.rs:238-254)."""
+
+    def __init__(self, big: np.ndarray, small: np.ndarray):
+        self.big, self.small = np.ascontiguousarray(big, dtype=np.uint64), np.ascontiguousarray(small, dtype=np.uint64)
+
+    @staticmethod
+    def from_bincode(buf: bytes) -> "ClientKey":
+        big, small = np.empty(2048, dtype=np.uint64), np.empty(742, dtype=np.uint64)
+        raw = np.frombuffer(buf, dtype=np.uint8)
+        rc = lib().fb_client_key_from_bincode(_p(np.ascontiguousarray(raw)), len(buf), _p(big), _p(small))
+        if rc != FB_OK:
+            _raise(rc, "malformed client key")
+        return ClientKey(big, small)
+
+    @staticmethod
+    def load(path: str) -> "ClientKey":
+        with open(path, "rb") as f:
+            return ClientKey.from_bincode(f.read())
+
+    def encrypt_block(self, m: int, seed: int = 1, stream: int = 0) -> np.ndarray:
+        out = np.empty(BIG, dtype=np.uint64)
+        lib().fb_client_encrypt_block(_p(self.big), m, seed, stream, _p(out))
+        return out
+
+    def encrypt_blocks(self, msgs, seed: int = 1, stream0: int = 0) -> np.ndarray:
+        out = np.empty((len(msgs), BIG), dtype=np.uint64)
+        for i, m in enumerate(msgs):
+            lib().fb_client_encrypt_block(_p(self.big), int(m), seed, stream0 + i, _p(out[i]))
+        return out
+
+    def decrypt_block(self, ct: np.ndarray) -> int:
+        return int(lib().fb_client_decrypt_block(_p(self.big), _p(np.ascontiguousarray(ct))))
+
+    def phase(self, ct: np.ndarray) -> int:
+        return int(lib().fb_client_phase(_p(self.big), 2048, _p(np.ascontiguousarray(ct))))
+
+    def decrypt(self, radix_ct: np.ndarray) -> int:
+        """RadixClientKey::decrypt (mod.rs:17)."""
+        return int(lib().fb_client_decrypt_radix(_p(self.big), _p(np.ascontiguousarray(radix_ct))))
+
+
+def encrypt_str(client_key: ClientKey, s: str, seed: int = 1) -> np.ndarray:
+    """encrypt_str (ciphertext.rs:32-40): [len, 4, 2049] u64; ValueError on non-ASCII."""
+    b = s.encode("latin-1", errors="replace") if s.isascii() else None
+    if b is None:
+        raise ValueError("content contains non-ascii characters")
+    out = np.empty((len(b), 4, BIG), dtype=np.uint64)
+    raw = np.frombuffer(b, dtype=np.uint8) if len(b) else np.zeros(0, dtype=np.uint8)
+    rc = lib().fb_client_encrypt_str(_p(client_key.big), _p(np.ascontiguousarray(raw)), len(b), seed, _p(out))
+    if rc != FB_OK:
+        raise ValueError("content contains non-ascii characters")
+    return out
+
+
+def trivial_str(s: str) -> np.ndarray:
+    """create_trivial_radix per byte (ciphertext.rs:8-30), as the reference's tests do (engine.rs:282-286)."""
+    b = s.encode("latin-1")
+    out = np.empty((len(b), 4, BIG), dtype=np.uint64)
+    raw = np.frombuffer(b, dtype=np.uint8) if len(b) else np.zeros(0, dtype=np.uint8)
+    lib().fb_client_trivial_str(_p(np.ascontiguousarray(raw)), len(b), _p(out))
+    return out
+
+
+def keygen_server_raw(client_key: ClientKey, seed: int = 0):
+    """ServerKey::new(&client_key) (engine.rs:252) -> (ksk [2048,5,743], bsk_std [742,1,2,2,2048])."""
+    ksk = np.empty((2048, 5, 743), dtype=np.uint64)
+    bsk = np.empty((742, 1, 2, 2, 2048), dtype=np.uint64)
+    rc = lib().fb_client_keygen_server(_p(client_key.big), _p(client_key.small), seed, _p(ksk), _p(bsk))
+    if rc != FB_OK:
+        _raise(rc, "keygen failed")
+    return ksk, bsk
+
+
+# -------------------------------------------------------------------------------------------------
+# GPU surface
+# -------------------------------------------------------------------------------------------------
+class ServerKey:
+    """The server key resident on one B200 (KSK + Fourier BSK in HBM) plus the evaluation context."""
+
+    def __init__(self, ksk: np.ndarray, bsk_std: np.ndarray, device: int = 0):
+        L = lib()
+        self._h = C.c_void_p()
+        rc = L.fb_ctx_create(C.byref(self._h), device)
+        if rc != FB_OK:
+            msg = L.fb_last_error(None).decode()
+            self._h = None
+            raise FbError(rc, msg)
+        ksk = np.ascontiguousarray(ksk, dtype=np.uint64)
+        bsk_std = np.ascontiguousarray(bsk_std, dtype=np.uint64)
+        assert ksk.size == KSK_WORDS and bsk_std.size == BSK_WORDS
+        self._check(L.fb_load_server_key_raw(self._h, _p(ksk), _p(bsk_std)))
+
+    def _check(self, rc):
+        if rc != FB_OK:
+            _raise(rc, lib().fb_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().fb_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stream(self) -> int:
+        return int(lib().fb_ctx_stream(self._h) or 0)
+
+    def sync(self):
+        self._check(lib().fb_sync(self._h))
+
+    def fourier_bsk(self) -> np.ndarray:
+        out = np.empty((742, 2, 2, 1024, 2), dtype=np.float64)
+        self._check(lib().fb_get_fourier_bsk(self._h, _p(out)))
+        return out
+
+    def keyswitch(self, cts: np.ndarray) -> np.ndarray:
+        cts = np.ascontiguousarray(cts.reshape(-1, BIG), dtype=np.uint64)
+        out = np.empty((cts.shape[0], SMALL), dtype=np.uint64)
+        self._check(lib().fb_keyswitch_batch(self._h, _p(cts), cts.shape[0], _p(out)))
+        return out
+
+    def pbs(self, cts: np.ndarray, luts: np.ndarray, lut_idx) -> np.ndarray:
+        cts = np.ascontiguousarray(cts.reshape(-1, BIG), dtype=np.uint64)
+        luts = np.ascontiguousarray(luts.reshape(-1, POLY), dtype=np.uint64)
+        idx = np.ascontiguousarray(np.asarray(lut_idx, dtype=np.uint32))
+        assert idx.shape[0] == cts.shape[0]
+        out = np.empty_like(cts)
+        self._check(lib().fb_pbs_batch(self._h, _p(cts), _p(luts), luts.shape[0], _p(idx), cts.shape[0], _p(out)))
+        return out
+
+    def bootstrap_small(self, small: np.ndarray, luts: np.ndarray, lut_idx) -> np.ndarray:
+        small = np.ascontiguousarray(small.reshape(-1, SMALL), dtype=np.uint64)
+        luts = np.ascontiguousarray(luts.reshape(-1, POLY), dtype=np.uint64)
+        idx = np.ascontiguousarray(np.asarray(lut_idx, dtype=np.uint32))
+        out = np.empty((small.shape[0], BIG), dtype=np.uint64)
+        self._check(lib().fb_bootstrap_small_batch(self._h, _p(small), _p(luts), luts.shape[0], _p(idx), small.shape[0], _p(out)))
+        return out
+
+    def pbs_dev(self, d_in: int, d_luts: int, d_lut_idx: int, count: int, d_out: int):
+        """device pointers (e.g. torch tensor .data_ptr()); asynchronous on self.stream"""
+        self._check(lib().fb_pbs_batch_dev(self._h, d_in, d_luts, d_lut_idx, count, d_out))
+
+    def timing(self, on: bool):
+        self._check(lib().fb_kernel_timing_enable(self._h, int(on)))
+
+    def kernel_stats(self, reset: bool = False) -> dict:
+        st = KernelStats()
+        self._check(lib().fb_kernel_stats_get(self._h, C.byref(st)))
+        if reset:
+            self._check(lib().fb_kernel_stats_reset(self._h))
+        return st.as_dict()
+
+    def or_fold(self, booleans: np.ndarray) -> np.ndarray:
+        booleans = np.ascontiguousarray(booleans.reshape(-1, BIG), dtype=np.uint64)
+        out = np.empty((4, BIG), dtype=np.uint64)
+        self._check(lib().fb_or_fold(self._h, _p(booleans), booleans.shape[0], _p(out)))
+        return out
+
+
+def has_match(server_key: ServerKey, content: np.ndarray, pattern: str, return_stats: bool = False, rank: int = 0, world: int = 1):
+    """has_match(&ServerKey, &[RadixCiphertext], &str) -> Result<RadixCiphertext> (engine.rs:8-42).
+
+    content: [n, 4, 2049] u64 (encrypt_str layout).  Returns a radix ciphertext [4, 2049] whose
+    decryption (ClientKey.decrypt) is 0/1.  Raises ParseError like the reference's Err, ReferencePanic
+    where the reference would panic."""
+    content = np.ascontiguousarray(content, dtype=np.uint64)
+    n = content.shape[0] if content.ndim == 3 else 0
+    out = np.empty((4, BIG), dtype=np.uint64)
+    st = MatchStats()
+    rc = lib().fb_has_match_shard(server_key._h, _p(content) if n else None, n, pattern.encode("latin-1"), rank, world, _p(out), C.byref(st))
+    server_key._check(rc)
+    return (out, st.as_dict()) if return_stats else out

@@ -1,0 +1,273 @@
+// api.cu -- context management and the batched keyswitch / bootstrap entry points of the C ABI
+// (include/fhe_b200.h).  No CPU fallback: every compute entry point needs an sm_100 device.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include "context.h"
+
+using fb::c2;
+
+int fb_fail(fb_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+int fb_cuda_fail(fb_ctx* ctx, cudaError_t e, const char* what) {
+  return fb_fail(ctx, FB_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+int fb_reserve(fb_ctx* ctx, fb_devbuf& b, size_t bytes) {
+  if (bytes <= b.cap) return FB_OK;
+  if (b.p) {
+    FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    FB_CUDA(ctx, cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+  }
+  size_t cap = bytes + bytes / 4;
+  FB_CUDA(ctx, cudaMalloc(&b.p, cap));
+  b.cap = cap;
+  return FB_OK;
+}
+
+static thread_local std::string g_create_err;
+
+extern "C" int fb_ctx_create(fb_ctx** out, int device) {
+  if (!out) return FB_ERR_ARG;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0 || device < 0 || device >= n) {
+    g_create_err = "no CUDA device available (libfhe_b200 has no CPU fallback)";
+    return FB_ERR_NO_DEVICE;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) {
+    g_create_err = "device is not compute capability 10.x (kernels are built for sm_100a only)";
+    return FB_ERR_NO_DEVICE;
+  }
+  fb_ctx* ctx = new (std::nothrow) fb_ctx();
+  if (!ctx) return FB_ERR_ARG;
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    g_create_err = "cudaSetDevice / cudaStreamCreate failed";
+    return FB_ERR_CUDA;
+  }
+  // twiddle tables
+  std::vector<c2> tabs(2 * fb::kTabEntries * 32);
+  fb::make_twiddle_tables(tabs.data(), tabs.data() + fb::kTabEntries * 32);
+  if (cudaMalloc(&ctx->d_tabs, tabs.size() * sizeof(c2)) != cudaSuccess ||
+      cudaMemcpy(ctx->d_tabs, tabs.data(), tabs.size() * sizeof(c2), cudaMemcpyHostToDevice) != cudaSuccess) {
+    delete ctx;
+    g_create_err = "twiddle table upload failed";
+    return FB_ERR_CUDA;
+  }
+  *out = ctx;
+  return FB_OK;
+}
+
+extern "C" void fb_ctx_destroy(fb_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& p : ctx->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+  for (auto& p : ctx->pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+  cudaFree(ctx->d_ksk);
+  cudaFree(ctx->d_fbsk);
+  cudaFree(ctx->d_tabs);
+  for (fb_devbuf* b : {&ctx->in, &ctx->small, &ctx->out, &ctx->luts, &ctx->lut_idx}) cudaFree(b->p);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+extern "C" const char* fb_last_error(const fb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+extern "C" void* fb_ctx_stream(fb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+extern "C" int fb_sync(fb_ctx* ctx) {
+  if (!ctx) return FB_ERR_ARG;
+  FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FB_OK;
+}
+
+extern "C" int fb_load_server_key_raw(fb_ctx* ctx, const uint64_t* h_ksk, const uint64_t* h_bsk_std) {
+  if (!ctx || !h_ksk || !h_bsk_std) return fb_fail(ctx, FB_ERR_ARG, "null argument");
+  FB_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->d_ksk) FB_CUDA(ctx, cudaMalloc(&ctx->d_ksk, FB_KSK_WORDS * sizeof(uint64_t)));
+  if (!ctx->d_fbsk) FB_CUDA(ctx, cudaMalloc(&ctx->d_fbsk, (size_t)fb::kLweN * 4 * fb::kHalfN * sizeof(c2)));
+  FB_CUDA(ctx, cudaMemcpyAsync(ctx->d_ksk, h_ksk, FB_KSK_WORDS * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+  uint64_t* d_std = nullptr;
+  FB_CUDA(ctx, cudaMalloc(&d_std, FB_BSK_WORDS * sizeof(uint64_t)));
+  cudaError_t e = cudaMemcpyAsync(d_std, h_bsk_std, FB_BSK_WORDS * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = fb::launch_bsk_convert(d_std, ctx->d_fbsk, ctx->d_tabs, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_std);
+  if (e != cudaSuccess) return fb_cuda_fail(ctx, e, "key upload / Fourier conversion");
+  ctx->have_key = true;
+  return FB_OK;
+}
+
+extern "C" int fb_get_fourier_bsk(fb_ctx* ctx, double* h_out) {
+  if (!ctx || !h_out) return fb_fail(ctx, FB_ERR_ARG, "null argument");
+  if (!ctx->have_key) return fb_fail(ctx, FB_ERR_NO_KEY, "server key not loaded");
+  FB_CUDA(ctx, cudaMemcpyAsync(h_out, ctx->d_fbsk, (size_t)fb::kLweN * 4 * fb::kHalfN * sizeof(c2), cudaMemcpyDeviceToHost, ctx->stream));
+  FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FB_OK;
+}
+
+// ---- timed launches ---------------------------------------------------------------------------
+static bool timing_begin(fb_ctx* ctx, int kind, fb_event_pair& ev) {
+  if (!ctx->timing) return false;
+  if (!ctx->pool.empty()) {
+    ev = ctx->pool.back();
+    ctx->pool.pop_back();
+  } else if (cudaEventCreate(&ev.a) != cudaSuccess || cudaEventCreate(&ev.b) != cudaSuccess) {
+    return false;
+  }
+  ev.kind = kind;
+  cudaEventRecord(ev.a, ctx->stream);
+  return true;
+}
+static void timing_end(fb_ctx* ctx, bool on, fb_event_pair& ev) {
+  if (!on) return;
+  cudaEventRecord(ev.b, ctx->stream);
+  ctx->pending.push_back(ev);
+}
+
+int fb_run_keyswitch(fb_ctx* ctx, const uint64_t* d_in, const int32_t* d_in_rows, uint64_t* d_small, int count) {
+  fb_event_pair ev;
+  bool t = timing_begin(ctx, 0, ev);
+  cudaError_t e = fb::launch_keyswitch(ctx->d_ksk, d_in, d_in_rows, d_small, count, ctx->stream);
+  timing_end(ctx, t, ev);
+  if (e != cudaSuccess) return fb_cuda_fail(ctx, e, "keyswitch_kernel launch");
+  ctx->ks.ks_launches++;
+  ctx->ks.ks_samples += count;
+  return FB_OK;
+}
+int fb_run_blind_rotate(fb_ctx* ctx, const uint64_t* d_small, const uint64_t* d_luts, const uint32_t* d_lut_idx,
+                        uint64_t* d_out, const int32_t* d_out_rows, int count) {
+  fb_event_pair ev;
+  bool t = timing_begin(ctx, 1, ev);
+  cudaError_t e = fb::launch_blind_rotate(ctx->d_fbsk, d_small, d_luts, d_lut_idx, d_out, d_out_rows, ctx->d_tabs, count, ctx->stream);
+  timing_end(ctx, t, ev);
+  if (e != cudaSuccess) return fb_cuda_fail(ctx, e, "blind_rotate_kernel launch");
+  ctx->ks.br_launches++;
+  ctx->ks.br_samples += count;
+  return FB_OK;
+}
+int fb_run_lincomb(fb_ctx* ctx, uint64_t* d_arena, const int32_t* out_rows, const int32_t* term_off,
+                   const int32_t* term_rows, const int64_t* term_coef, const uint64_t* body_const, int n_out) {
+  fb_event_pair ev;
+  bool t = timing_begin(ctx, 2, ev);
+  cudaError_t e = fb::launch_lincomb(d_arena, out_rows, term_off, term_rows, term_coef, body_const, n_out, ctx->stream);
+  timing_end(ctx, t, ev);
+  if (e != cudaSuccess) return fb_cuda_fail(ctx, e, "lincomb_kernel launch");
+  ctx->ks.lin_launches++;
+  return FB_OK;
+}
+
+extern "C" int fb_kernel_timing_enable(fb_ctx* ctx, int on) {
+  if (!ctx) return FB_ERR_ARG;
+  ctx->timing = on != 0;
+  return FB_OK;
+}
+static int resolve_pending(fb_ctx* ctx) {
+  FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (auto& p : ctx->pending) {
+    float ms = 0.f;
+    FB_CUDA(ctx, cudaEventElapsedTime(&ms, p.a, p.b));
+    if (p.kind == 0) ctx->ks.ks_ms += ms;
+    else if (p.kind == 1) ctx->ks.br_ms += ms;
+    else ctx->ks.lin_ms += ms;
+    ctx->pool.push_back(p);
+  }
+  ctx->pending.clear();
+  return FB_OK;
+}
+extern "C" int fb_kernel_stats_reset(fb_ctx* ctx) {
+  if (!ctx) return FB_ERR_ARG;
+  int rc = resolve_pending(ctx);
+  ctx->ks = fb_kernel_stats{};
+  return rc;
+}
+extern "C" int fb_kernel_stats_get(fb_ctx* ctx, fb_kernel_stats* out) {
+  if (!ctx || !out) return FB_ERR_ARG;
+  int rc = resolve_pending(ctx);
+  *out = ctx->ks;
+  return rc;
+}
+
+// ---- batch entry points ---------------------------------------------------------------------------
+extern "C" int fb_keyswitch_batch(fb_ctx* ctx, const uint64_t* h_in, size_t count, uint64_t* h_out) {
+  if (!ctx || !h_in || !h_out) return fb_fail(ctx, FB_ERR_ARG, "null argument");
+  if (!ctx->have_key) return fb_fail(ctx, FB_ERR_NO_KEY, "server key not loaded");
+  if (count == 0) return FB_OK;
+  FB_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = fb_reserve(ctx, ctx->in, count * FB_LWE_BIG_WORDS * 8))) return rc;
+  if ((rc = fb_reserve(ctx, ctx->small, count * FB_LWE_SMALL_WORDS * 8))) return rc;
+  FB_CUDA(ctx, cudaMemcpyAsync(ctx->in.p, h_in, count * FB_LWE_BIG_WORDS * 8, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = fb_run_keyswitch(ctx, (const uint64_t*)ctx->in.p, nullptr, (uint64_t*)ctx->small.p, (int)count))) return rc;
+  FB_CUDA(ctx, cudaMemcpyAsync(h_out, ctx->small.p, count * FB_LWE_SMALL_WORDS * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FB_OK;
+}
+
+extern "C" int fb_pbs_batch_dev(fb_ctx* ctx, const uint64_t* d_in, const uint64_t* d_luts, const uint32_t* d_lut_idx,
+                                size_t count, uint64_t* d_out) {
+  if (!ctx || !d_in || !d_luts || !d_lut_idx || !d_out) return fb_fail(ctx, FB_ERR_ARG, "null argument");
+  if (!ctx->have_key) return fb_fail(ctx, FB_ERR_NO_KEY, "server key not loaded");
+  if (count == 0) return FB_OK;
+  FB_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = fb_reserve(ctx, ctx->small, count * FB_LWE_SMALL_WORDS * 8))) return rc;
+  if ((rc = fb_run_keyswitch(ctx, d_in, nullptr, (uint64_t*)ctx->small.p, (int)count))) return rc;
+  return fb_run_blind_rotate(ctx, (const uint64_t*)ctx->small.p, d_luts, d_lut_idx, d_out, nullptr, (int)count);
+}
+
+static int upload_luts(fb_ctx* ctx, const uint64_t* h_luts, size_t n_luts, const uint32_t* h_lut_idx, size_t count) {
+  for (size_t b = 0; b < count; b++)
+    if (h_lut_idx[b] >= n_luts) return fb_fail(ctx, FB_ERR_ARG, "lut index out of range");
+  int rc;
+  if ((rc = fb_reserve(ctx, ctx->luts, n_luts * FB_POLY_SIZE * 8))) return rc;
+  if ((rc = fb_reserve(ctx, ctx->lut_idx, count * 4))) return rc;
+  FB_CUDA(ctx, cudaMemcpyAsync(ctx->luts.p, h_luts, n_luts * FB_POLY_SIZE * 8, cudaMemcpyHostToDevice, ctx->stream));
+  FB_CUDA(ctx, cudaMemcpyAsync(ctx->lut_idx.p, h_lut_idx, count * 4, cudaMemcpyHostToDevice, ctx->stream));
+  return FB_OK;
+}
+
+extern "C" int fb_pbs_batch(fb_ctx* ctx, const uint64_t* h_in, const uint64_t* h_luts, size_t n_luts,
+                            const uint32_t* h_lut_idx, size_t count, uint64_t* h_out) {
+  if (!ctx || !h_in || !h_luts || !h_lut_idx || !h_out || n_luts == 0) return fb_fail(ctx, FB_ERR_ARG, "null argument");
+  if (!ctx->have_key) return fb_fail(ctx, FB_ERR_NO_KEY, "server key not loaded");
+  if (count == 0) return FB_OK;
+  FB_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = upload_luts(ctx, h_luts, n_luts, h_lut_idx, count))) return rc;
+  if ((rc = fb_reserve(ctx, ctx->in, count * FB_LWE_BIG_WORDS * 8))) return rc;
+  if ((rc = fb_reserve(ctx, ctx->out, count * FB_LWE_BIG_WORDS * 8))) return rc;
+  FB_CUDA(ctx, cudaMemcpyAsync(ctx->in.p, h_in, count * FB_LWE_BIG_WORDS * 8, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = fb_pbs_batch_dev(ctx, (const uint64_t*)ctx->in.p, (const uint64_t*)ctx->luts.p, (const uint32_t*)ctx->lut_idx.p,
+                             count, (uint64_t*)ctx->out.p)))
+    return rc;
+  FB_CUDA(ctx, cudaMemcpyAsync(h_out, ctx->out.p, count * FB_LWE_BIG_WORDS * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FB_OK;
+}
+
+extern "C" int fb_bootstrap_small_batch(fb_ctx* ctx, const uint64_t* h_small, const uint64_t* h_luts, size_t n_luts,
+                                        const uint32_t* h_lut_idx, size_t count, uint64_t* h_out) {
+  if (!ctx || !h_small || !h_luts || !h_lut_idx || !h_out || n_luts == 0) return fb_fail(ctx, FB_ERR_ARG, "null argument");
+  if (!ctx->have_key) return fb_fail(ctx, FB_ERR_NO_KEY, "server key not loaded");
+  if (count == 0) return FB_OK;
+  FB_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = upload_luts(ctx, h_luts, n_luts, h_lut_idx, count))) return rc;
+  if ((rc = fb_reserve(ctx, ctx->small, count * FB_LWE_SMALL_WORDS * 8))) return rc;
+  if ((rc = fb_reserve(ctx, ctx->out, count * FB_LWE_BIG_WORDS * 8))) return rc;
+  FB_CUDA(ctx, cudaMemcpyAsync(ctx->small.p, h_small, count * FB_LWE_SMALL_WORDS * 8, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = fb_run_blind_rotate(ctx, (const uint64_t*)ctx->small.p, (const uint64_t*)ctx->luts.p, (const uint32_t*)ctx->lut_idx.p,
+                                (uint64_t*)ctx->out.p, nullptr, (int)count)))
+    return rc;
+  FB_CUDA(ctx, cudaMemcpyAsync(h_out, ctx->out.p, count * FB_LWE_BIG_WORDS * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FB_OK;
+}

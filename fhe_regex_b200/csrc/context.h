@@ -1,0 +1,52 @@
+// context.h -- fb_ctx: per-GPU state behind the C ABI (include/fhe_b200.h).  Internal.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/fhe_b200.h"
+#include "kernels.h"
+
+struct fb_devbuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+struct fb_event_pair {
+  cudaEvent_t a, b;
+  int kind;  // 0 ks, 1 br, 2 lin
+};
+
+struct fb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  // keys
+  uint64_t* d_ksk = nullptr;
+  fb::c2* d_fbsk = nullptr;
+  fb::c2* d_tabs = nullptr;
+  bool have_key = false;
+  // scratch for the batch entry points
+  fb_devbuf in, small, out, luts, lut_idx;
+  // timing
+  bool timing = false;
+  std::vector<fb_event_pair> pending;
+  std::vector<fb_event_pair> pool;
+  fb_kernel_stats ks{};
+};
+
+int fb_fail(fb_ctx* ctx, int code, const std::string& msg);
+int fb_cuda_fail(fb_ctx* ctx, cudaError_t e, const char* what);
+int fb_reserve(fb_ctx* ctx, fb_devbuf& b, size_t bytes);
+#define FB_CUDA(ctx, call)                                        \
+  do {                                                            \
+    cudaError_t _e = (call);                                      \
+    if (_e != cudaSuccess) return fb_cuda_fail(ctx, _e, #call);   \
+  } while (0)
+
+// timed launches on ctx->stream (timing is a no-op unless enabled)
+int fb_run_keyswitch(fb_ctx* ctx, const uint64_t* d_in, const int32_t* d_in_rows, uint64_t* d_small, int count);
+int fb_run_blind_rotate(fb_ctx* ctx, const uint64_t* d_small, const uint64_t* d_luts, const uint32_t* d_lut_idx,
+                        uint64_t* d_out, const int32_t* d_out_rows, int count);
+int fb_run_lincomb(fb_ctx* ctx, uint64_t* d_arena, const int32_t* out_rows, const int32_t* term_off,
+                   const int32_t* term_rows, const int64_t* term_coef, const uint64_t* body_const, int n_out);

@@ -1,0 +1,297 @@
+// kernels.cu -- sm_100a kernels of the batched programmable bootstrap (KS -> BR -> SE) and glue.
+//
+// Replaces the tfhe-rs 0.2.0 arithmetic under fhe-regex's six smart_* call sites
+// (/root/reference/src/regex/execution.rs:76,93,110,143,173,190) -- SURVEY.md section 2, kernels K1-K5, K7.
+//   K1 keyswitch_kernel          exact mod-2^64 LWE x KSK gadget contraction
+//   K2-K4 blind_rotate_kernel    modulus switch + LUT accumulator init, 742 CMUX steps with an f64
+//                                 negacyclic FFT external product, sample extract -- one launch
+//   K5 lincomb_kernel            sum_i c_i * ct_i + trivial(const)
+//   K7 bsk_convert_kernel        standard-domain bootstrapping key -> Fourier domain (key load)
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "br_core.cuh"
+#include "kernels.h"
+
+namespace fb {
+
+__device__ __forceinline__ void bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7: key conversion.  One CTA (2 warps) per (i, row): the two polynomials of one GLWE row.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64, 1)
+bsk_convert_kernel(const uint64_t* __restrict__ bsk_std, c2* __restrict__ fbsk, const c2* __restrict__ tabs_g) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  c2* tbuf = reinterpret_cast<c2*>(smem);            // [2][1024]
+  c2* tab_f = tbuf + 2 * kHalfN;                      // [12][32]
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  for (int t = tid; t < kTabEntries * 32; t += 64) tab_f[t] = tabs_g[t];
+  __syncthreads();
+  const size_t row = blockIdx.x;  // (i * 2 + r)
+  double xr[32], xi[32];
+  phaseA_load_torus(xr, xi, bsk_std + (row * 2 + w) * kN, lane);
+  fft32_dif(xr, xi);
+  fwd_twiddle_store(xr, xi, tbuf + w * kHalfN, tab_f, lane);
+  __syncthreads();
+  const int pp = lane >> 4, k1 = 16 * w + (lane & 15);
+  phaseB_load(xr, xi, tbuf + pp * kHalfN, k1);
+  fft32_dif(xr, xi);
+  c2* dst = fbsk + (row * 2 + pp) * kHalfN + k1;
+#pragma unroll
+  for (int q = 0; q < 32; q++) {
+    c2 v;
+    v.x = xr[q];
+    v.y = xi[q];
+    dst[32 * brev5(q)] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: keyswitch.  out[b][c] = [c==742]*in[b][2048] - sum_{i<2048} sum_{l<5} d(b,i,l) * KSK[i][l][c]
+// CTA tile: KS_TB samples x 256 output columns; the KSK slice is read once per tile and reused
+// across the KS_TB samples held in registers; digits are decomposed once per chunk into smem.
+// ------------------------------------------------------------------------------------------------
+constexpr int KS_TB = 8;
+constexpr int KS_CH = 256;
+
+__device__ __forceinline__ uint32_t ks_pack_digits(uint64_t x) {
+  // closest representable on the top 15 bits, then 5 balanced base-8 digits, least significant first;
+  // the digit produced at iteration t multiplies KSK level row l = 4 - t (rows are stored most
+  // significant level first).  Packed as 5 signed nibbles, nibble l = digit for row l.
+  uint32_t state = (uint32_t)((((x >> 48) + 1ull) >> 1) & 0x7FFFull);
+  uint32_t packed = 0;
+#pragma unroll
+  for (int t = 0; t < kKsLevels; t++) {
+    uint32_t res = state & 7u;
+    state >>= 3;
+    uint32_t carry = (((res - 1u) | state) & res) >> 2;
+    state += carry;
+    uint32_t digit = (res - (carry << 3)) & 0xFu;
+    packed |= digit << (4 * (kKsLevels - 1 - t));
+  }
+  return packed;
+}
+
+__global__ void __launch_bounds__(256)
+keyswitch_kernel(const uint64_t* __restrict__ ksk, const uint64_t* __restrict__ in, const int32_t* __restrict__ in_rows,
+                 uint64_t* __restrict__ out, int count) {
+  __shared__ uint32_t dig[KS_TB][KS_CH];
+  __shared__ const uint64_t* src[KS_TB];
+  const int tid = threadIdx.x;
+  const int b0 = blockIdx.x * KS_TB;
+  const int col = blockIdx.y * 256 + tid;
+  const bool col_ok = col < kSmall;
+  const int colc = col_ok ? col : kSmall - 1;
+  if (tid < KS_TB) {
+    int b = b0 + tid;
+    if (b >= count) b = count - 1;
+    const size_t row = in_rows ? (size_t)in_rows[b] : (size_t)b;
+    src[tid] = in + row * kBig;
+  }
+  __syncthreads();
+  uint64_t acc[KS_TB];
+#pragma unroll
+  for (int b = 0; b < KS_TB; b++) acc[b] = 0;
+
+  for (int chunk = 0; chunk < kN / KS_CH; chunk++) {
+#pragma unroll
+    for (int b = 0; b < KS_TB; b++) dig[b][tid] = ks_pack_digits(src[b][chunk * KS_CH + tid]);
+    __syncthreads();
+    const uint64_t* kp = ksk + ((size_t)chunk * KS_CH * kKsLevels) * kSmall + colc;
+#pragma unroll 2
+    for (int ii = 0; ii < KS_CH; ii++) {
+      uint64_t k[kKsLevels];
+#pragma unroll
+      for (int l = 0; l < kKsLevels; l++) k[l] = __ldg(kp + ((size_t)ii * kKsLevels + l) * kSmall);
+#pragma unroll
+      for (int b = 0; b < KS_TB; b++) {
+        const int32_t p = (int32_t)dig[b][ii];
+#pragma unroll
+        for (int l = 0; l < kKsLevels; l++) {
+          const int32_t d = (p << (28 - 4 * l)) >> 28;  // sign-extended nibble l
+          acc[b] -= (uint64_t)(int64_t)d * k[l];
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (col_ok) {
+#pragma unroll
+    for (int b = 0; b < KS_TB; b++) {
+      if (b0 + b < count) {
+        uint64_t v = acc[b];
+        if (col == kLweN) v += src[b][kN];
+        out[(size_t)(b0 + b) * kSmall + col] = v;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2-K4: blind rotation.  S samples per CTA, 2 warps per sample (warp w owns polynomial w in the
+// coefficient-domain phases and rows 16w..16w+15 of both polynomials in the frequency-domain phase).
+// Shared memory per CTA: S * (32 KiB accumulator + 32 KiB transpose buffer) + 12 KiB twiddles
+// + S * 1.5 KiB mod-switched mask.
+// ------------------------------------------------------------------------------------------------
+template <int S>
+__global__ void __launch_bounds__(64 * S, 1)
+blind_rotate_kernel(const c2* __restrict__ fbsk, const uint64_t* __restrict__ small, const uint64_t* __restrict__ luts,
+                    const uint32_t* __restrict__ lut_idx, uint64_t* __restrict__ out, const int32_t* __restrict__ out_rows,
+                    const c2* __restrict__ tabs_g, int count) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  uint64_t* acc_all = reinterpret_cast<uint64_t*>(smem);                    // [S][2][2048]
+  c2* tbuf_all = reinterpret_cast<c2*>(smem + (size_t)S * 32768);            // [S][2][1024]
+  c2* tab_f = reinterpret_cast<c2*>(smem + (size_t)S * 65536);               // [12][32]
+  c2* tab_i = tab_f + kTabEntries * 32;                                      // [12][32]
+  uint16_t* at_all = reinterpret_cast<uint16_t*>(tab_i + kTabEntries * 32);  // [S][768]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int s = warp >> 1, w = warp & 1;
+  const int sample = blockIdx.x * S + s;
+  const bool active = sample < count;
+
+  for (int t = tid; t < 2 * kTabEntries * 32; t += 64 * S) tab_f[t] = tabs_g[t];
+  uint16_t* at = at_all + s * 768;
+  if (active) {
+    const uint64_t* sm = small + (size_t)sample * kSmall;
+    for (int t = w * 32 + lane; t < kSmall; t += 64) {
+      const uint64_t x = sm[t];
+      uint32_t a = modswitch(x);
+      if (t < kLweN) a = (a & 4095u) | ((x != 0 && (a & 4095u) != 0) ? 0x8000u : 0u);
+      at[t] = (uint16_t)a;
+    }
+  }
+  __syncthreads();
+  if (!active) return;
+
+  uint64_t* accp = acc_all + (size_t)s * 2 * kN + (size_t)w * kN;  // polynomial w of this sample
+  c2* tbuf = tbuf_all + (size_t)s * 2 * kHalfN;
+  const int bar_id = 1 + s;
+
+  // accumulator init: (0, lut * X^{-b})
+  {
+    const uint64_t* lut = luts + (size_t)lut_idx[sample] * kN;
+    const uint32_t rot = (4096u - (uint32_t)at[kLweN]) & 4095u;
+    for (int j = lane; j < kN; j += 32) accp[j] = (w == 0) ? 0ull : rot_read(lut, (uint32_t)j, rot);
+  }
+  __syncwarp();
+
+  double xr[32], xi[32];
+  const int pp = lane >> 4, k1 = 16 * w + (lane & 15);
+  for (int i = 0; i < kLweN; i++) {
+    const uint32_t a = at[i];
+    if (!(a & 0x8000u)) continue;  // warp- and sample-uniform: zero mask element (trivial inputs) or X^0
+    // phase A: this warp's polynomial -> digits -> folded/twisted -> pass 1 -> transpose buffer
+    phaseA_load(xr, xi, accp, a & 4095u, lane);
+    fft32_dif(xr, xi);
+    fwd_twiddle_store(xr, xi, tbuf + w * kHalfN, tab_f, lane);
+    bar_sync(bar_id, 64);
+    // phase B: rows -> pass 2 -> Fourier MAC with GGSW_i -> inverse pass 1 -> transpose buffer
+    phaseB_load(xr, xi, tbuf + pp * kHalfN, k1);
+    fft32_dif(xr, xi);
+    {
+      const c2* b_own = fbsk + fbsk_index(i, pp, pp, k1);
+      const c2* b_oth = fbsk + fbsk_index(i, pp, 1 - pp, k1);
+#pragma unroll
+      for (int q = 0; q < 32; q++) {
+        const int k2 = brev5(q);
+        const c2 bo = __ldg(b_own + 32 * k2);
+        const c2 bx = __ldg(b_oth + 32 * k2);
+        double kr, ki, sr, si;
+        mac_point(xr[q], xi[q], bo, bx, kr, ki, sr, si);
+        xr[q] = kr + __shfl_xor_sync(0xffffffffu, sr, 16);
+        xi[q] = ki + __shfl_xor_sync(0xffffffffu, si, 16);
+      }
+    }
+    fft32_dit_inv(xr, xi);
+    inv_twiddle_store(xr, xi, tbuf + pp * kHalfN, tab_i, k1);
+    bar_sync(bar_id, 64);
+    // phase C: columns -> inverse pass 2 -> untwist, round to torus, accumulate
+    phaseC_load(xr, xi, tbuf + w * kHalfN, lane);
+    fft32_dit_inv(xr, xi);
+    phaseC_update(xr, xi, accp, lane);
+    __syncwarp();
+  }
+
+  // K4: sample extract of the constant coefficient
+  bar_sync(bar_id, 64);
+  {
+    const uint64_t* am = acc_all + (size_t)s * 2 * kN;
+    const uint64_t* ab = am + kN;
+    const size_t row = out_rows ? (size_t)out_rows[sample] : (size_t)sample;
+    uint64_t* o = out + row * kBig;
+    for (int j = w * 32 + lane; j < kN; j += 64) o[j] = (j == 0) ? am[0] : (uint64_t)0 - am[kN - j];
+    if (w == 0 && lane == 0) o[kN] = ab[0];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: linear glue.  out[row_o] = sum_t coef[t] * arena[row_t] + (0,...,0, body_const[o])
+// terms of output o are term_off[o] .. term_off[o+1]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+lincomb_kernel(uint64_t* __restrict__ arena, const int32_t* __restrict__ out_rows, const int32_t* __restrict__ term_off,
+               const int32_t* __restrict__ term_rows, const int64_t* __restrict__ term_coef,
+               const uint64_t* __restrict__ body_const, int n_out) {
+  const int o = blockIdx.x;
+  if (o >= n_out) return;
+  const int t0 = term_off[o], t1 = term_off[o + 1];
+  uint64_t* dst = arena + (size_t)out_rows[o] * kBig;
+  for (int j = threadIdx.x; j < kBig; j += 256) {
+    uint64_t v = (j == kN) ? body_const[o] : 0ull;
+    for (int t = t0; t < t1; t++) v += (uint64_t)term_coef[t] * arena[(size_t)term_rows[t] * kBig + j];
+    dst[j] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+size_t br_smem_bytes(int S) { return (size_t)S * 65536 + 2 * kTabEntries * 32 * sizeof(c2) + (size_t)S * 768 * sizeof(uint16_t); }
+
+cudaError_t launch_bsk_convert(const uint64_t* bsk_std, c2* fbsk, const c2* tabs, cudaStream_t st) {
+  const size_t smem = 2 * kHalfN * sizeof(c2) + kTabEntries * 32 * sizeof(c2);
+  cudaError_t e = cudaFuncSetAttribute(bsk_convert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  bsk_convert_kernel<<<kLweN * 2, 64, smem, st>>>(bsk_std, fbsk, tabs);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_keyswitch(const uint64_t* ksk, const uint64_t* in, const int32_t* in_rows, uint64_t* out, int count,
+                             cudaStream_t st) {
+  if (count <= 0) return cudaSuccess;
+  dim3 grid((count + KS_TB - 1) / KS_TB, (kSmall + 255) / 256);
+  keyswitch_kernel<<<grid, 256, 0, st>>>(ksk, in, in_rows, out, count);
+  return cudaGetLastError();
+}
+
+template <int S>
+static cudaError_t launch_br_s(const c2* fbsk, const uint64_t* small, const uint64_t* luts, const uint32_t* lut_idx,
+                               uint64_t* out, const int32_t* out_rows, const c2* tabs, int count, cudaStream_t st) {
+  const size_t smem = br_smem_bytes(S);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(blind_rotate_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  blind_rotate_kernel<S><<<(count + S - 1) / S, 64 * S, smem, st>>>(fbsk, small, luts, lut_idx, out, out_rows, tabs, count);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_blind_rotate(const c2* fbsk, const uint64_t* small, const uint64_t* luts, const uint32_t* lut_idx,
+                                uint64_t* out, const int32_t* out_rows, const c2* tabs, int count, cudaStream_t st) {
+  if (count <= 0) return cudaSuccess;
+  return launch_br_s<3>(fbsk, small, luts, lut_idx, out, out_rows, tabs, count, st);
+}
+
+cudaError_t launch_lincomb(uint64_t* arena, const int32_t* out_rows, const int32_t* term_off, const int32_t* term_rows,
+                           const int64_t* term_coef, const uint64_t* body_const, int n_out, cudaStream_t st) {
+  if (n_out <= 0) return cudaSuccess;
+  lincomb_kernel<<<n_out, 256, 0, st>>>(arena, out_rows, term_off, term_rows, term_coef, body_const, n_out);
+  return cudaGetLastError();
+}
+
+}  // namespace fb

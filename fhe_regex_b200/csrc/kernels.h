@@ -1,0 +1,16 @@
+// kernels.h -- launchers of the sm_100a kernels in kernels.cu (internal; the public boundary is include/fhe_b200.h)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "br_core.cuh"
+
+namespace fb {
+size_t br_smem_bytes(int S);
+cudaError_t launch_bsk_convert(const uint64_t* bsk_std, c2* fbsk, const c2* tabs, cudaStream_t st);
+cudaError_t launch_keyswitch(const uint64_t* ksk, const uint64_t* in, const int32_t* in_rows, uint64_t* out, int count,
+                             cudaStream_t st);
+cudaError_t launch_blind_rotate(const c2* fbsk, const uint64_t* small, const uint64_t* luts, const uint32_t* lut_idx,
+                                uint64_t* out, const int32_t* out_rows, const c2* tabs, int count, cudaStream_t st);
+cudaError_t launch_lincomb(uint64_t* arena, const int32_t* out_rows, const int32_t* term_off, const int32_t* term_rows,
+                           const int64_t* term_coef, const uint64_t* body_const, int n_out, cudaStream_t st);
+}  // namespace fb

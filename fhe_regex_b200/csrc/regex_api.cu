@@ -1,0 +1,204 @@
+// regex_api.cu -- has_match() behind the C ABI: build the level-synchronous PBS plan on the host
+// (regex_host.cpp) and run it on the GPU, every level as lincomb -> keyswitch -> blind-rotate launches
+// on the context stream with no host synchronisation in between.
+//
+// Replaces has_match (engine.rs:8-42) + Execution (execution.rs:37-223) of the reference.
+#include <cuda_runtime.h>
+#include <cstring>
+#include <vector>
+#include "context.h"
+#include "regex_host.h"
+
+using namespace fbre;
+
+namespace {
+
+struct DevPlan {
+  // all per-level arrays concatenated into one upload each
+  std::vector<int32_t> i32;
+  std::vector<int64_t> i64;
+  std::vector<uint64_t> u64;
+  std::vector<uint32_t> u32;
+  struct Off { size_t lin_out, lin_off, lin_rows, lin_coef, lin_const, in_rows, lut_idx; int n_lin, n_pbs; int32_t out_base; };
+  std::vector<Off> levels;
+};
+
+void flatten_plan(const Plan& plan, DevPlan& d) {
+  for (auto& l : plan.levels) {
+    DevPlan::Off o;
+    o.n_lin = (int)l.lin_out_rows.size();
+    o.n_pbs = (int)l.in_rows.size();
+    o.out_base = l.out_row_base;
+    o.lin_out = d.i32.size(); d.i32.insert(d.i32.end(), l.lin_out_rows.begin(), l.lin_out_rows.end());
+    o.lin_off = d.i32.size(); d.i32.insert(d.i32.end(), l.lin_term_off.begin(), l.lin_term_off.end());
+    o.lin_rows = d.i32.size(); d.i32.insert(d.i32.end(), l.lin_term_rows.begin(), l.lin_term_rows.end());
+    o.in_rows = d.i32.size(); d.i32.insert(d.i32.end(), l.in_rows.begin(), l.in_rows.end());
+    o.lin_coef = d.i64.size(); d.i64.insert(d.i64.end(), l.lin_coef.begin(), l.lin_coef.end());
+    o.lin_const = d.u64.size(); d.u64.insert(d.u64.end(), l.lin_const.begin(), l.lin_const.end());
+    o.lut_idx = d.u32.size(); d.u32.insert(d.u32.end(), l.lut_idx.begin(), l.lut_idx.end());
+    d.levels.push_back(o);
+  }
+}
+
+struct ScopedDev {
+  std::vector<void*> ptrs;
+  ~ScopedDev() { for (void* p : ptrs) cudaFree(p); }
+  template <class T>
+  cudaError_t alloc(T** out, size_t n) {
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, (n ? n : 1) * sizeof(T));
+    if (e == cudaSuccess) ptrs.push_back(p);
+    *out = (T*)p;
+    return e;
+  }
+};
+
+// fixed accumulator table (shortint generate_accumulator layout), LutId order
+void build_lut_table(std::vector<uint64_t>& luts) {
+  luts.resize((size_t)LUT_COUNT * FB_POLY_SIZE);
+  for (uint32_t id = 0; id < LUT_COUNT; id++) {
+    uint64_t f16[16];
+    for (uint32_t x = 0; x < 16; x++) f16[x] = lut_value(id, x);
+    fb_make_lut(f16, luts.data() + (size_t)id * FB_POLY_SIZE);
+  }
+}
+
+void write_trivial_radix(uint64_t* h_out, uint64_t bit) {
+  std::memset(h_out, 0, sizeof(uint64_t) * 4 * FB_LWE_BIG_WORDS);
+  h_out[FB_POLY_SIZE] = bit << 59;
+}
+
+// run a plan; content (n_in_rows x 2049) is uploaded to arena rows [0, n_in_rows)
+int run_plan(fb_ctx* ctx, const Plan& plan, const uint64_t* h_in, size_t n_in_rows, uint64_t* h_out_radix, double* gpu_ms) {
+  if (plan.result_kind < 2) {
+    write_trivial_radix(h_out_radix, (uint64_t)plan.result_kind);
+    if (gpu_ms) *gpu_ms = 0;
+    return FB_OK;
+  }
+  if (!ctx->have_key) return fb_fail(ctx, FB_ERR_NO_KEY, "server key not loaded");
+  FB_CUDA(ctx, cudaSetDevice(ctx->device));
+  DevPlan d;
+  flatten_plan(plan, d);
+  ScopedDev dev;
+  uint64_t *d_arena = nullptr, *d_u64 = nullptr, *d_luts = nullptr, *d_small = nullptr;
+  int32_t* d_i32 = nullptr;
+  int64_t* d_i64 = nullptr;
+  uint32_t* d_u32 = nullptr;
+  std::vector<uint64_t> luts;
+  build_lut_table(luts);
+  FB_CUDA(ctx, dev.alloc(&d_arena, (size_t)plan.n_rows * FB_LWE_BIG_WORDS));
+  FB_CUDA(ctx, dev.alloc(&d_small, (size_t)(plan.stats.max_level_width + 1) * FB_LWE_SMALL_WORDS));
+  FB_CUDA(ctx, dev.alloc(&d_i32, d.i32.size()));
+  FB_CUDA(ctx, dev.alloc(&d_i64, d.i64.size()));
+  FB_CUDA(ctx, dev.alloc(&d_u64, d.u64.size()));
+  FB_CUDA(ctx, dev.alloc(&d_u32, d.u32.size()));
+  FB_CUDA(ctx, dev.alloc(&d_luts, luts.size()));
+  cudaStream_t st = ctx->stream;
+  cudaEvent_t ev0, ev1;
+  FB_CUDA(ctx, cudaEventCreate(&ev0));
+  FB_CUDA(ctx, cudaEventCreate(&ev1));
+  auto cleanup = [&]() { cudaEventDestroy(ev0); cudaEventDestroy(ev1); };
+#define RP_CUDA(call)                                                         \
+  do {                                                                        \
+    cudaError_t _e = (call);                                                  \
+    if (_e != cudaSuccess) { cleanup(); return fb_cuda_fail(ctx, _e, #call); } \
+  } while (0)
+  RP_CUDA(cudaMemcpyAsync(d_arena, h_in, n_in_rows * FB_LWE_BIG_WORDS * 8, cudaMemcpyHostToDevice, st));
+  RP_CUDA(cudaMemcpyAsync(d_i32, d.i32.data(), d.i32.size() * 4, cudaMemcpyHostToDevice, st));
+  RP_CUDA(cudaMemcpyAsync(d_i64, d.i64.data(), d.i64.size() * 8, cudaMemcpyHostToDevice, st));
+  RP_CUDA(cudaMemcpyAsync(d_u64, d.u64.data(), d.u64.size() * 8, cudaMemcpyHostToDevice, st));
+  RP_CUDA(cudaMemcpyAsync(d_u32, d.u32.data(), d.u32.size() * 4, cudaMemcpyHostToDevice, st));
+  RP_CUDA(cudaMemcpyAsync(d_luts, luts.data(), luts.size() * 8, cudaMemcpyHostToDevice, st));
+  RP_CUDA(cudaEventRecord(ev0, st));
+  for (auto& o : d.levels) {
+    int rc;
+    if (o.n_lin > 0) {
+      rc = fb_run_lincomb(ctx, d_arena, d_i32 + o.lin_out, d_i32 + o.lin_off, d_i32 + o.lin_rows, d_i64 + o.lin_coef,
+                          d_u64 + o.lin_const, o.n_lin);
+      if (rc) { cleanup(); return rc; }
+    }
+    if (o.n_pbs > 0) {
+      rc = fb_run_keyswitch(ctx, d_arena, d_i32 + o.in_rows, d_small, o.n_pbs);
+      if (rc) { cleanup(); return rc; }
+      rc = fb_run_blind_rotate(ctx, d_small, d_luts, d_u32 + o.lut_idx, d_arena + (size_t)o.out_base * FB_LWE_BIG_WORDS, nullptr, o.n_pbs);
+      if (rc) { cleanup(); return rc; }
+    }
+  }
+  RP_CUDA(cudaEventRecord(ev1, st));
+  std::memset(h_out_radix, 0, sizeof(uint64_t) * 4 * FB_LWE_BIG_WORDS);
+  RP_CUDA(cudaMemcpyAsync(h_out_radix, d_arena + (size_t)plan.result_row * FB_LWE_BIG_WORDS, FB_LWE_BIG_WORDS * 8, cudaMemcpyDeviceToHost, st));
+  RP_CUDA(cudaStreamSynchronize(st));
+  float ms = 0.f;
+  RP_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+  if (gpu_ms) *gpu_ms = ms;
+  cleanup();
+#undef RP_CUDA
+  return FB_OK;
+}
+
+}  // namespace
+
+extern "C" int fb_parse_debug(const char* pattern, char* out, size_t cap) {
+  if (!pattern || !out || cap == 0) return FB_ERR_ARG;
+  RegExpr re;
+  std::string err;
+  int rc = parse(pattern, re, err);
+  const std::string s = rc == FB_OK ? debug_fmt(re) : err;
+  const size_t n = s.size() < cap - 1 ? s.size() : cap - 1;
+  std::memcpy(out, s.data(), n);
+  out[n] = 0;
+  return rc;
+}
+
+extern "C" int fb_plan_stats(const char* pattern, size_t n_chars, fb_match_stats* stats) {
+  if (!pattern || !stats) return FB_ERR_ARG;
+  Plan plan;
+  std::string err;
+  int rc = build_plan(pattern, n_chars, 0, 1, plan, err);
+  if (rc != FB_OK) return rc;
+  *stats = plan.stats;
+  return FB_OK;
+}
+
+extern "C" int fb_plan_eval_plain(const char* pattern, const uint8_t* content, size_t n_chars, int rank, int world, int* result) {
+  if (!pattern || !result || (!content && n_chars)) return FB_ERR_ARG;
+  Plan plan;
+  std::string err;
+  int rc = build_plan(pattern, n_chars, rank, world, plan, err);
+  if (rc != FB_OK) return rc;
+  return eval_plan_plain(plan, content, 0, result, err);
+}
+
+extern "C" int fb_has_match_shard(fb_ctx* ctx, const uint64_t* h_content, size_t n_chars, const char* pattern, int rank,
+                                  int world, uint64_t* h_out, fb_match_stats* stats) {
+  if (!ctx || !pattern || !h_out || (!h_content && n_chars)) return fb_fail(ctx, FB_ERR_ARG, "null argument");
+  Plan plan;
+  std::string err;
+  int rc = build_plan(pattern, n_chars, rank, world, plan, err);
+  if (rc != FB_OK) return fb_fail(ctx, rc, err);
+  double ms = 0;
+  rc = run_plan(ctx, plan, h_content, 4 * n_chars, h_out, &ms);
+  if (rc != FB_OK) return rc;
+  if (stats) {
+    *stats = plan.stats;
+    stats->gpu_ms = ms;
+  }
+  return FB_OK;
+}
+
+extern "C" int fb_has_match(fb_ctx* ctx, const uint64_t* h_content, size_t n_chars, const char* pattern, uint64_t* h_out,
+                            fb_match_stats* stats) {
+  return fb_has_match_shard(ctx, h_content, n_chars, pattern, 0, 1, h_out, stats);
+}
+
+extern "C" int fb_or_fold(fb_ctx* ctx, const uint64_t* h_in, size_t n, uint64_t* h_out) {
+  if (!ctx || !h_out || (!h_in && n)) return fb_fail(ctx, FB_ERR_ARG, "null argument");
+  if (n == 1) {
+    std::memset(h_out, 0, sizeof(uint64_t) * 4 * FB_LWE_BIG_WORDS);
+    std::memcpy(h_out, h_in, sizeof(uint64_t) * FB_LWE_BIG_WORDS);
+    return FB_OK;
+  }
+  Plan plan;
+  build_or_fold_plan(n, plan);
+  return run_plan(ctx, plan, h_in, n, h_out, nullptr);
+}

@@ -1,0 +1,159 @@
+/*
+ * fhe_b200.h -- C ABI of libfhe_b200.so: the B200-native TFHE evaluation backend behind fhe-regex's
+ * execution hot path.
+ *
+ * The reference (RKlompUU/fhe-regex) has NO FFI/plugin boundary: `Execution` holds a concrete
+ * `tfhe::integer::ServerKey` (src/regex/execution.rs:38) and calls its methods.  The boundary below is
+ * therefore introduced at exactly the tfhe-rs symbols the reference touches; each entry
+ * point cites the reference call site it replaces.  A Rust shim binds these with `extern "C"` (see
+ * INTEGRATION.md); tests and bench bind them with ctypes.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative FB_ERR_* code; nothing throws or aborts
+ *     across the boundary; fb_last_error() gives the message of the last failure on that context.
+ *   - plain pointers + sizes only.  Pointers named h_* are caller-owned HOST buffers, read/written
+ *     only during the call.  Pointers named d_* are DEVICE pointers on the context's GPU.
+ *   - one host thread drives one context; one context drives one GPU (one process per GPU).
+ *   - there is no CPU fallback: fb_ctx_create fails without an sm_100 device.
+ *
+ * Ciphertext / key layouts (PARAM_MESSAGE_2_CARRY_2, 4 radix blocks; ciphertext.rs:42-45):
+ *   LWE (big key)    2049 x u64 : mask[2048], body          -- a shortint block under the big key
+ *   LWE (small key)   743 x u64 : mask[742], body
+ *   radix ciphertext 4 x 2049 x u64, block 0 = least significant 2 bits (ciphertext.rs:8-30)
+ *   KSK  [2048][5][743] u64   level rows most-significant first (tfhe-rs LweKeyswitchKey)
+ *   BSK  [742][1][2][2][2048] u64 standard domain: [lwe bit][level][row][polynomial][coefficient]
+ *   LUT  [2048] u64 accumulator body polynomial (tfhe-rs shortint generate_accumulator)
+ */
+#ifndef FHE_B200_H
+#define FHE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FB_LWE_BIG_WORDS 2049
+#define FB_LWE_SMALL_WORDS 743
+#define FB_POLY_SIZE 2048
+#define FB_RADIX_BLOCKS 4
+#define FB_KSK_WORDS (2048ull * 5ull * 743ull)
+#define FB_BSK_WORDS (742ull * 2ull * 2ull * 2048ull)
+
+#define FB_OK 0
+#define FB_ERR_NO_DEVICE (-1)   /* no CUDA device of compute capability 10.x */
+#define FB_ERR_CUDA (-2)        /* a CUDA runtime call failed */
+#define FB_ERR_ARG (-3)         /* invalid argument */
+#define FB_ERR_NO_KEY (-4)      /* server key not loaded */
+#define FB_ERR_PARSE (-5)       /* pattern does not parse: anyhow::Error of parse(), parser.rs:146-184 */
+#define FB_ERR_PANIC (-6)       /* the reference would panic on this input (engine.rs:189-190, parser.rs:349-351) */
+#define FB_ERR_FORMAT (-7)      /* malformed serialized key */
+
+typedef struct fb_ctx fb_ctx;
+
+/* ---- context ---------------------------------------------------------------------------------- */
+/* Replaces holding a `ServerKey` by value (engine.rs:20 `Execution::new(sk.clone())`). */
+int fb_ctx_create(fb_ctx** out, int device);
+void fb_ctx_destroy(fb_ctx* ctx);
+const char* fb_last_error(const fb_ctx* ctx);
+/* cudaStream_t every kernel of this context is launched on (for external event timing / sync) */
+void* fb_ctx_stream(fb_ctx* ctx);
+int fb_sync(fb_ctx* ctx);
+
+/* ---- server key ------------------------------------------------------------------------------- */
+/* Replaces `ServerKey::new(&client_key)` / `gen_keys_radix` output being handed to has_match
+ * (engine.rs:252, ciphertext.rs:44, mod.rs:16).  Uploads the KSK, converts the BSK to the Fourier
+ * domain on the device (tfhe-rs convert_standard_lwe_bootstrap_key_to_fourier). */
+int fb_load_server_key_raw(fb_ctx* ctx, const uint64_t* h_ksk, const uint64_t* h_bsk_std);
+/* read back the Fourier BSK ([742][2][2][1024] complex f64, natural frequency order) -- tests only */
+int fb_get_fourier_bsk(fb_ctx* ctx, double* h_out);
+
+/* ---- hot path: batched keyswitch / programmable bootstrap ------------------------------------- */
+/* K1 alone, exposed for the bit-exact gate.  Under every smart_* (execution.rs:76-190):
+ * tfhe-rs keyswitch_lwe_ciphertext.  h_in[count][2049] -> h_out[count][743] */
+int fb_keyswitch_batch(fb_ctx* ctx, const uint64_t* h_in, size_t count, uint64_t* h_out);
+/* KS -> blind rotate -> sample extract (shortint keyswitch_programmable_bootstrap), one LUT per input.
+ * h_in[count][2049], h_luts[n_luts][2048], h_lut_idx[count] -> h_out[count][2049] */
+int fb_pbs_batch(fb_ctx* ctx, const uint64_t* h_in, const uint64_t* h_luts, size_t n_luts, const uint32_t* h_lut_idx,
+                 size_t count, uint64_t* h_out);
+/* blind rotate + sample extract on already keyswitched inputs h_small[count][743] (stage-wise parity) */
+int fb_bootstrap_small_batch(fb_ctx* ctx, const uint64_t* h_small, const uint64_t* h_luts, size_t n_luts,
+                             const uint32_t* h_lut_idx, size_t count, uint64_t* h_out);
+/* same as fb_pbs_batch on DEVICE buffers, asynchronous on fb_ctx_stream(); the context's scratch is
+ * grown as needed.  d_in[count][2049], d_luts[n_luts][2048], d_lut_idx[count] -> d_out[count][2049] */
+int fb_pbs_batch_dev(fb_ctx* ctx, const uint64_t* d_in, const uint64_t* d_luts, const uint32_t* d_lut_idx, size_t count,
+                     uint64_t* d_out);
+
+/* ---- regex entry point ------------------------------------------------------------------------ */
+typedef struct fb_match_stats {
+  uint64_t variants;        /* branches produced by build_branches over all start offsets (engine.rs:15-18) */
+  uint64_t ct_ops;          /* cache-missing homomorphic ops, what engine.rs:36-40 logs */
+  uint64_t cache_hits;      /* engine.rs:36-40 */
+  uint64_t ops_eq, ops_gt, ops_le, ops_and, ops_or, ops_not; /* ct_ops by type */
+  uint64_t pbs;             /* programmable bootstraps executed by this backend */
+  uint64_t levels;          /* dependent PBS levels (kernel launch rounds) */
+  uint64_t max_level_width; /* widest PBS batch */
+  double gpu_ms;            /* device time of the evaluation (CUDA events on the context stream) */
+} fb_match_stats;
+
+/* Replaces `has_match(&ServerKey, &[RadixCiphertext], &str) -> Result<RadixCiphertext>` (engine.rs:8-42).
+ * h_content[n_chars][4][2049] (encrypt_str layout, ciphertext.rs:32-40), pattern NUL-terminated.
+ * h_out[4][2049]: block 0 encrypts 0/1, blocks 1-3 are trivial zeros, so RadixClientKey::decrypt
+ * (mod.rs:17) returns the same 0/1 as the reference.  stats may be NULL. */
+int fb_has_match(fb_ctx* ctx, const uint64_t* h_content, size_t n_chars, const char* pattern, uint64_t* h_out,
+                 fb_match_stats* stats);
+/* rank's share of the variants (start offsets i with i % world == rank); partial results are OR-folded
+ * with fb_or_fold after an all-gather */
+int fb_has_match_shard(fb_ctx* ctx, const uint64_t* h_content, size_t n_chars, const char* pattern, int rank, int world,
+                       uint64_t* h_out, fb_match_stats* stats);
+/* OR of n single-block booleans h_in[n][2049] -> h_out[4][2049] radix (the final fold, engine.rs:30-33) */
+int fb_or_fold(fb_ctx* ctx, const uint64_t* h_in, size_t n, uint64_t* h_out);
+
+/* Parser surface kept from the reference: parse() (parser.rs:146).  Writes the `{:?}` rendering of
+ * the RegExpr (parser.rs:87-144) into out (NUL-terminated, truncated to cap).  No GPU needed. */
+int fb_parse_debug(const char* pattern, char* out, size_t cap);
+/* plaintext dry run of the variant generator + executor bookkeeping (no ciphertexts, no GPU):
+ * fills variants / ct_ops / cache_hits / ops_* / pbs / levels / max_level_width. */
+int fb_plan_stats(const char* pattern, size_t n_chars, fb_match_stats* stats);
+
+/* plaintext dry run of the lowered circuit on cleartext content bytes (host only, no ciphertexts):
+ * result = what decrypt(has_match(..)) would give for this rank's share; used to test the lowering. */
+int fb_plan_eval_plain(const char* pattern, const uint8_t* content, size_t n_chars, int rank, int world, int* result);
+
+/* ---- timing ----------------------------------------------------------------------------------- */
+typedef struct fb_kernel_stats {
+  uint64_t ks_launches, br_launches, lin_launches;
+  uint64_t ks_samples, br_samples;
+  double ks_ms, br_ms, lin_ms; /* summed CUDA-event durations on the context stream */
+} fb_kernel_stats;
+/* per-kernel CUDA-event timing of every launch since the last reset (events are resolved at call time,
+ * which synchronizes the stream) */
+int fb_kernel_stats_reset(fb_ctx* ctx);
+int fb_kernel_stats_get(fb_ctx* ctx, fb_kernel_stats* out);
+int fb_kernel_timing_enable(fb_ctx* ctx, int on);
+
+/* ---- client-side glue (tests / bench / demo only; not on the server hot path) ------------------ */
+/* Deserialize a bincode RadixClientKey like test_data/client_key (engine.rs:248-251).
+ * Writes big[2048], small[742] secret key bits. */
+int fb_client_key_from_bincode(const uint8_t* buf, size_t len, uint64_t* big_key, uint64_t* small_key);
+/* ServerKey::new(&client_key) (engine.rs:252): fresh KSK/BSK from the secret keys, seeded test PRNG */
+int fb_client_keygen_server(const uint64_t* big_key, const uint64_t* small_key, uint64_t seed, uint64_t* h_ksk,
+                            uint64_t* h_bsk_std);
+/* RadixClientKey::encrypt per byte (ciphertext.rs:32-40): h_out[n][4][2049]; fails on non-ASCII */
+int fb_client_encrypt_str(const uint64_t* big_key, const uint8_t* bytes, size_t n, uint64_t seed, uint64_t* h_out);
+/* create_trivial_radix per byte (ciphertext.rs:8-30), what the reference's tests feed (engine.rs:282-286) */
+int fb_client_trivial_str(const uint8_t* bytes, size_t n, uint64_t* h_out);
+/* shortint block: encrypt message m (4 bits, message+carry) / phase / decrypt */
+int fb_client_encrypt_block(const uint64_t* big_key, uint64_t m, uint64_t seed, uint64_t stream, uint64_t* h_out);
+uint64_t fb_client_phase(const uint64_t* key, size_t dim, const uint64_t* ct);
+uint64_t fb_client_decrypt_block(const uint64_t* big_key, const uint64_t* ct);
+/* RadixClientKey::decrypt (mod.rs:17): sum of blocks * 4^i mod 256 */
+uint64_t fb_client_decrypt_radix(const uint64_t* big_key, const uint64_t* ct);
+/* shortint generate_accumulator: f16[i] = f(i) for i < 16 -> lut[2048] */
+int fb_make_lut(const uint64_t* f16, uint64_t* lut);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FHE_B200_H */

@@ -442,3 +442,18 @@ int orc_max_threads(void) {
   return 1;
 #endif
 }
+
+/* test helper: out = round(a (*) b) negacyclic through the oracle's own f64 FFT; a small signed ints, b torus */
+void orc_negacyclic_mul_fft(const i64 *a, const u64 *b, u64 *out) {
+  fft_init();
+  double pa[GLWE_N], pb[GLWE_N], ar[HALF_N], ai[HALF_N], br[HALF_N], bi[HALF_N], p[GLWE_N];
+  for (int j = 0; j < GLWE_N; j++) { pa[j] = (double)a[j]; pb[j] = (double)(i64)b[j] * (1.0 / 18446744073709551616.0); }
+  nfft_forward(pa, ar, ai);
+  nfft_forward(pb, br, bi);
+  for (int k = 0; k < HALF_N; k++) {
+    double r = ar[k] * br[k] - ai[k] * bi[k], im = ar[k] * bi[k] + ai[k] * br[k];
+    ar[k] = r; ai[k] = im;
+  }
+  nfft_backward(ar, ai, p);
+  for (int j = 0; j < GLWE_N; j++) out[j] = from_torus(p[j]);
+}
