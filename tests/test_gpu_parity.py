@@ -1,0 +1,182 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+  keyswitch            bit-exact (integer work)
+  bootstrap            decrypt-exact + output noise within the stated bound (floating point: the
+                       f64 FFT makes ciphertext bits implementation-defined, so parity is phase-level)
+  has_match            decrypted 0/1 identical to the reference's semantics (oracle/regex_plain.py) and
+                       to the reference's own 25 engine vectors (tests/golden/engine_cases.json)
+"""
+import ctypes
+import json
+import os
+
+import numpy as np
+import pytest
+
+import fhe_regex_b200 as fb
+from oracle import regex_plain as rp
+from oracle import tfhe
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+ENGINE_CASES = json.load(open(os.path.join(GOLDEN, "engine_cases.json")))["cases"]
+
+# stated tolerance for one bootstrap output (torus fraction): sigma_out ~ 3e-5;
+# |err| < 4e-4 is > 10 sigma, and far below the half-box 1/32 that would flip a decryption.
+PBS_ERR_MAX = 4e-4
+PBS_ERR_STD_MAX = 8e-5
+
+
+@pytest.fixture(scope="module")
+def gpu_key(server_key):
+    sk = fb.ServerKey(server_key.ksk, server_key.bsk)
+    yield sk
+    sk.close()
+
+
+@pytest.fixture(scope="module")
+def fck():
+    return fb.ClientKey.load(os.path.join(GOLDEN, "client_key"))
+
+
+def test_keyswitch_bit_exact(client_key, server_key, gpu_key):
+    rng = np.random.default_rng(0)
+    cts = [tfhe.encrypt_batch(client_key, np.arange(37) % 16, seed=21)]
+    cts.append(rng.integers(0, 2 ** 64, size=(20, tfhe.BIG), dtype=np.uint64))       # arbitrary words
+    edge = np.zeros((6, tfhe.BIG), dtype=np.uint64)
+    edge[0, :] = np.uint64(2 ** 64 - 1)
+    edge[1, :] = np.uint64(1 << 48)            # rounding boundary of the decomposer
+    edge[2, :] = np.uint64((1 << 48) - 1)
+    edge[3, :] = np.uint64((4 << 49) + (4 << 52))  # digit ties
+    edge[4, 2048] = np.uint64(7 << 59)         # trivial
+    edge[5, ::2] = np.uint64(1 << 63)
+    cts.append(edge)
+    cts = np.concatenate(cts)
+    for count in (1, 7, 8, 9, cts.shape[0]):   # ragged against the 8-sample tile
+        got = gpu_key.keyswitch(cts[:count])
+        exp = tfhe.keyswitch(server_key, cts[:count])
+        assert (got == exp).all(), count
+
+
+def test_fourier_key_matches_emulation(server_key, gpu_key):
+    # the device key conversion against the lane-by-lane CPU emulation of the same kernel code
+    import subprocess
+    emu_dir = os.path.join(os.path.dirname(__file__), "emu")
+    so = os.path.join(emu_dir, "libemu_br.so")
+    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(os.path.join(emu_dir, "emu_br.cpp")):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-march=x86-64-v3", "-fPIC", "-shared", "-o", so, os.path.join(emu_dir, "emu_br.cpp")])
+    L = ctypes.CDLL(so)
+    exp = np.zeros((742, 2, 2, 1024, 2), dtype=np.float64)
+    L.emu_bsk_to_fourier(server_key.bsk.ctypes.data_as(ctypes.c_void_p), exp.ctypes.data_as(ctypes.c_void_p))
+    got = gpu_key.fourier_bsk()
+    scale = np.abs(exp).max()
+    assert np.abs(got - exp).max() < 1e-11 * scale
+
+
+def test_bootstrap_trivial_inputs_bit_exact(server_key, gpu_key):
+    # trivial ciphertexts (what the reference's tests use, engine.rs:282-286): every CMUX is skipped,
+    # the result is pure integer work -> bit-exact against the oracle
+    fs = [lambda x: x, lambda x: (3 * x) % 16, lambda x: int(x >= 1)]
+    luts = np.stack([tfhe.make_lut(f) for f in fs])
+    cts = np.stack([tfhe.trivial_shortint(m) for m in range(16)] * 3)
+    idx = np.repeat(np.arange(3), 16)
+    got = gpu_key.pbs(cts, luts, idx)
+    exp = tfhe.pbs(server_key, cts, luts, idx)
+    assert (got == exp).all()
+
+
+def test_bootstrap_decrypt_and_noise(client_key, server_key, gpu_key):
+    n = 444 * 2 + 5                                   # several CTAs, ragged tail
+    msgs = np.arange(n) % 16
+    cts = tfhe.encrypt_batch(client_key, msgs, seed=31)
+    fs = [lambda x: x, lambda x: (x * x) % 16, lambda x: int(x == 5), lambda x: int(x >= 1), lambda x: 15 - x]
+    luts = np.stack([tfhe.make_lut(f) for f in fs])
+    idx = (np.arange(n) // 16) % len(fs)
+    got = gpu_key.pbs(cts, luts, idx)
+    exp_msg = np.array([fs[i](int(m)) & 15 for m, i in zip(msgs, idx)], dtype=np.uint64)
+    ph = tfhe.phase_batch(client_key.big, got)
+    dec = ((ph + np.uint64(1 << 58)) >> np.uint64(59)) & np.uint64(15)
+    assert (dec == exp_msg).all()
+    err = tfhe.torus_err(ph, exp_msg << np.uint64(59))
+    assert np.abs(err).max() < PBS_ERR_MAX and err.std() < PBS_ERR_STD_MAX
+    # oracle on a subset of the same inputs: same decryptions, noise of the same order
+    sub = slice(0, 48)
+    ref = tfhe.pbs(server_key, cts[sub], luts, idx[sub])
+    ph_ref = tfhe.phase_batch(client_key.big, ref)
+    assert ((((ph_ref + np.uint64(1 << 58)) >> np.uint64(59)) & np.uint64(15)) == dec[sub]).all()
+    assert tfhe.torus_err(ph_ref, exp_msg[sub] << np.uint64(59)).std() < PBS_ERR_STD_MAX
+
+
+def test_bootstrap_stagewise_against_oracle(client_key, server_key, gpu_key):
+    # same keyswitched inputs into both blind rotations
+    msgs = np.arange(32) % 16
+    cts = tfhe.encrypt_batch(client_key, msgs, seed=41)
+    small = tfhe.keyswitch(server_key, cts)
+    lut = tfhe.make_lut(lambda x: (x + 1) % 16)
+    got = gpu_key.bootstrap_small(small, lut[None], np.zeros(32, dtype=np.uint32))
+    exp_msg = ((msgs + 1) % 16).astype(np.uint64)
+    for b in range(32):
+        ref = tfhe.bootstrap_small(server_key, small[b], lut)
+        assert tfhe.decrypt_shortint(client_key, got[b]) == tfhe.decrypt_shortint(client_key, ref) == int(exp_msg[b])
+    err = tfhe.torus_err(tfhe.phase_batch(client_key.big, got), exp_msg << np.uint64(59))
+    assert np.abs(err).max() < PBS_ERR_MAX
+
+
+def test_empty_batches(gpu_key):
+    assert gpu_key.keyswitch(np.zeros((0, tfhe.BIG), dtype=np.uint64)).shape == (0, tfhe.SMALL)
+    lut = tfhe.make_lut(lambda x: x)
+    assert gpu_key.pbs(np.zeros((0, tfhe.BIG), dtype=np.uint64), lut[None], np.zeros(0, dtype=np.uint32)).shape == (0, tfhe.BIG)
+
+
+@pytest.mark.parametrize("case", ENGINE_CASES, ids=["%s~%s" % (c["content"], c["pattern"]) for c in ENGINE_CASES])
+def test_has_match_reference_vectors_trivial(case, fck, gpu_key):
+    # exactly the reference's test_has_match (engine.rs:256-291): trivial content, decrypt, compare
+    ct = fb.trivial_str(case["content"])
+    res = fb.has_match(gpu_key, ct, case["pattern"])
+    assert fck.decrypt(res) == case["expected"]
+
+
+REAL_CASES = [
+    ("abc", "/^abc$/"), ("abd", "/^abc$/"),
+    ("aBc", "/^abc$/i"), ("aBc" + "x" * 13, "/^abc$/i"), ("xxaBcxxxxxxxxxxx", "/abc/i"),
+    ("bq.", r"/^[a-d][^x-z]\.$/"), ("aq.", r"/^[a-d][^x-z]\.$/"), ("bx.", r"/^[a-d][^x-z]\.$/"), ("by.", r"/^[a-d][^x-z]\.$/"),
+    ("abbc", "/^ab{2,4}c$/"), ("abbbbc", "/^ab{2,4}c$/"), ("abc", "/^ab{2,4}c$/"), ("abbbbbc", "/^ab{2,4}c$/"),
+    ("aaa", "/^a{,2}$/"), ("", "/^$/"), ("zzz", "/./"), ("zzz", "/^.*$/"),
+]
+
+
+@pytest.mark.parametrize("content,pattern", REAL_CASES, ids=["%s~%s" % c for c in REAL_CASES])
+def test_has_match_real_encryption(content, pattern, fck, gpu_key):
+    ct = fb.encrypt_str(fck, content, seed=5)
+    res, st = fb.has_match(gpu_key, ct, pattern, return_stats=True)
+    exp, ex, nb = rp.has_match(content, pattern, return_exec=True)
+    assert fck.decrypt(res) == exp
+    assert (st["variants"], st["ct_ops"], st["cache_hits"]) == (nb, ex.ct_ops, ex.cache_hits)
+    assert (res[1:, :] == 0).all()  # blocks 1-3 trivial zero
+
+
+def test_has_match_64_char_configs(fck, gpu_key):
+    rng = np.random.default_rng(5)
+    c64 = "".join(rng.choice(list("abcx"), size=64))
+    planted = c64[:20] + "xaabc" + c64[25:]
+    for content, pattern in [(c64, r"/[a-d][^x-z]\./"), (planted, "/ab{2,4}c/"), (c64, "/ab{2,4}c/"), (planted, "/a+b?c/"),
+                             ("x" * 64, "/a+b?c/"), (c64, r"/^[a-d][^x-z]\.$/")]:
+        res = fb.has_match(gpu_key, fb.encrypt_str(fck, content, seed=9), pattern)
+        assert fck.decrypt(res) == rp.has_match(content, pattern), (content, pattern)
+
+
+def test_sharded_match_and_or_fold(fck, gpu_key):
+    content = "xxabbcxxxxaacxxx"
+    ct = fb.encrypt_str(fck, content, seed=2)
+    for pattern in ["/a+b?c/", "/^zz/", "/ab{2,4}c/"]:
+        world = 4
+        parts = np.stack([fb.has_match(gpu_key, ct, pattern, rank=r, world=world)[0] for r in range(world)])
+        assert fck.decrypt(gpu_key.or_fold(parts)) == rp.has_match(content, pattern)
+
+
+def test_errors_surface_like_the_reference(fck, gpu_key):
+    ct = fb.trivial_str("ab")
+    with pytest.raises(fb.ParseError):
+        fb.has_match(gpu_key, ct, "/a(b/")
+    with pytest.raises(fb.ReferencePanic):
+        fb.has_match(gpu_key, ct, "/^/")
