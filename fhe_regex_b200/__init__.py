@@ -89,6 +89,8 @@ def lib():
     L.fb_kernel_stats_reset.argtypes = [vp]
     L.fb_kernel_stats_get.argtypes = [vp, C.POINTER(KernelStats)]
     L.fb_kernel_timing_enable.argtypes = [vp, C.c_int]
+    L.fb_measure_fp64_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
+    L.fb_pbs_batch_quantum.argtypes = [vp]
     L.fb_client_key_from_bincode.argtypes = [vp, sz, vp, vp]
     L.fb_client_keygen_server.argtypes = [vp, vp, C.c_uint64, vp, vp]
     L.fb_client_encrypt_str.argtypes = [vp, vp, sz, C.c_uint64, vp]
@@ -312,6 +314,14 @@ class ServerKey:
         if reset:
             self._check(lib().fb_kernel_stats_reset(self._h))
         return st.as_dict()
+
+    def fp64_peak_tflops(self, reps: int = 5) -> float:
+        v = C.c_double(0)
+        self._check(lib().fb_measure_fp64_peak(self._h, reps, C.byref(v)))
+        return v.value
+
+    def pbs_quantum(self) -> int:
+        return int(lib().fb_pbs_batch_quantum(self._h))
 
     def or_fold(self, booleans: np.ndarray) -> np.ndarray:
         booleans = np.ascontiguousarray(booleans.reshape(-1, BIG), dtype=np.uint64)

@@ -1,6 +1,7 @@
 // api.cu -- context management and the batched keyswitch / bootstrap entry points of the C ABI
 // (include/fhe_b200.h).  No CPU fallback: every compute entry point needs an sm_100 device.
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -111,6 +112,45 @@ extern "C" int fb_get_fourier_bsk(fb_ctx* ctx, double* h_out) {
   FB_CUDA(ctx, cudaMemcpyAsync(h_out, ctx->d_fbsk, (size_t)fb::kLweN * 4 * fb::kHalfN * sizeof(c2), cudaMemcpyDeviceToHost, ctx->stream));
   FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return FB_OK;
+}
+
+// FP64 FMA pipe throughput of this device (TFLOP/s), best of `reps` launches timed with CUDA events
+extern "C" int fb_measure_fp64_peak(fb_ctx* ctx, int reps, double* tflops) {
+  if (!ctx || !tflops) return fb_fail(ctx, FB_ERR_ARG, "null argument");
+  FB_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaDeviceProp prop;
+  FB_CUDA(ctx, cudaGetDeviceProperties(&prop, ctx->device));
+  const int ctas = prop.multiProcessorCount * 8;
+  double* sink = nullptr;
+  FB_CUDA(ctx, cudaMalloc(&sink, 8));
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  double best = 0;
+  cudaError_t e = cudaSuccess;
+  for (int r = 0; r < reps + 2 && e == cudaSuccess; r++) {
+    cudaEventRecord(a, ctx->stream);
+    e = fb::launch_fp64_peak(sink, ctas, ctx->stream);
+    cudaEventRecord(b, ctx->stream);
+    if (e == cudaSuccess) e = cudaEventSynchronize(b);
+    float ms = 0;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, a, b);
+    if (e == cudaSuccess && r >= 2 && ms > 0) best = std::max(best, fb::fp64_peak_flops_per_launch(ctas) / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(sink);
+  if (e != cudaSuccess) return fb_cuda_fail(ctx, e, "fp64 peak probe");
+  *tflops = best;
+  return FB_OK;
+}
+
+// batch sizes that fill the GPU evenly are multiples of this (SM count x samples per CTA)
+extern "C" int fb_pbs_batch_quantum(fb_ctx* ctx) {
+  if (!ctx) return FB_ERR_ARG;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, ctx->device) != cudaSuccess) return FB_ERR_CUDA;
+  return prop.multiProcessorCount * fb::br_samples_per_cta();
 }
 
 // ---- timed launches ---------------------------------------------------------------------------

@@ -247,8 +247,36 @@ lincomb_kernel(uint64_t* __restrict__ arena, const int32_t* __restrict__ out_row
 }
 
 // ------------------------------------------------------------------------------------------------
+// FP64 FMA pipe probe: the roofline denominator of the blind rotation (MEASURED_PEAKS.json carries
+// HBM and bf16 figures only).  8 independent DFMA chains per thread, 2 flop per DFMA.
+// ------------------------------------------------------------------------------------------------
+constexpr int PEAK_ITERS = 4096;
+__global__ void __launch_bounds__(256)
+fp64_peak_kernel(double* __restrict__ sink, double seed) {
+  double a[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) a[k] = seed + (double)(threadIdx.x + k);
+  const double m = 1.0000001, c = 1e-9;
+  for (int it = 0; it < PEAK_ITERS; it++) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] = __fma_rn(a[k], m, c);
+  }
+  double s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) s += a[k];
+  if (s == 12345.678) sink[0] = s;  // never true; keeps the chains alive
+}
+
+// ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
+cudaError_t launch_fp64_peak(double* sink, int ctas, cudaStream_t st) {
+  fp64_peak_kernel<<<ctas, 256, 0, st>>>(sink, 0.5);
+  return cudaGetLastError();
+}
+double fp64_peak_flops_per_launch(int ctas) { return (double)ctas * 256.0 * 8.0 * 2.0 * (double)PEAK_ITERS; }
+int br_samples_per_cta() { return 3; }
+
 size_t br_smem_bytes(int S) { return (size_t)S * 65536 + 2 * kTabEntries * 32 * sizeof(c2) + (size_t)S * 768 * sizeof(uint16_t); }
 
 cudaError_t launch_bsk_convert(const uint64_t* bsk_std, c2* fbsk, const c2* tabs, cudaStream_t st) {

@@ -13,4 +13,7 @@ cudaError_t launch_blind_rotate(const c2* fbsk, const uint64_t* small, const uin
                                 uint64_t* out, const int32_t* out_rows, const c2* tabs, int count, cudaStream_t st);
 cudaError_t launch_lincomb(uint64_t* arena, const int32_t* out_rows, const int32_t* term_off, const int32_t* term_rows,
                            const int64_t* term_coef, const uint64_t* body_const, int n_out, cudaStream_t st);
+cudaError_t launch_fp64_peak(double* sink, int ctas, cudaStream_t st);
+double fp64_peak_flops_per_launch(int ctas);
+int br_samples_per_cta();
 }  // namespace fb

@@ -132,6 +132,11 @@ typedef struct fb_kernel_stats {
 int fb_kernel_stats_reset(fb_ctx* ctx);
 int fb_kernel_stats_get(fb_ctx* ctx, fb_kernel_stats* out);
 int fb_kernel_timing_enable(fb_ctx* ctx, int on);
+/* FP64 FMA-pipe throughput of the device in TFLOP/s (dependent-chain DFMA probe, best of reps): the
+ * roofline denominator of the blind rotation */
+int fb_measure_fp64_peak(fb_ctx* ctx, int reps, double* tflops);
+/* PBS batch sizes that fill the GPU evenly are multiples of this (SM count x samples per CTA) */
+int fb_pbs_batch_quantum(fb_ctx* ctx);
 
 /* ---- client-side glue (tests / bench / demo only; not on the server hot path) ------------------ */
 /* Deserialize a bincode RadixClientKey like test_data/client_key (engine.rs:248-251).
