@@ -207,6 +207,82 @@ FB_HD void phaseC_load(double (&xr)[32], double (&xi)[32], const c2* tbuf_p, int
   }
 }
 
+// ---- split transposes: the real and the imaginary planes go through one [2][1024] double buffer one
+// after the other (half the shared memory of a complex buffer; 4 two-warp barriers per transpose).
+// Same row/column swizzle as the complex versions: element (row k1, column c) of polynomial p lives at
+// p*1024 + k1*32 + (c ^ k1).
+
+// forward inter-pass twiddle in place: register q (row k1 = brev5(q)) *= exp(i*pi*lane*(1-4*k1)/2048)
+FB_HD void fwd_twiddle_inplace(double (&xr)[32], double (&xi)[32], const c2* tab_f, int lane) {
+  c2 lo[4];
+#pragma unroll
+  for (int l = 0; l < 4; l++) lo[l] = tab_f[l * 32 + lane];
+#pragma unroll
+  for (int h = 0; h < 8; h++) {
+    const c2 hi = tab_f[(4 + h) * 32 + lane];
+#pragma unroll
+    for (int l = 0; l < 4; l++) {
+      const int q = brev5(4 * h + l);
+      double tr = lo[l].x, ti = lo[l].y;
+      if (h != 0) {
+        tr = fb_fma(lo[l].x, hi.x, -(lo[l].y * hi.y));
+        ti = fb_fma(lo[l].x, hi.y, lo[l].y * hi.x);
+      }
+      const double yr = fb_fma(xr[q], tr, -(xi[q] * ti));
+      xi[q] = fb_fma(xr[q], ti, xi[q] * tr);
+      xr[q] = yr;
+    }
+  }
+}
+// column writer (thread = column `lane` of polynomial p, register q = row brev5(q))
+FB_HD void col_store_brev(const double (&x)[32], double* plane_p, int lane) {
+#pragma unroll
+  for (int q = 0; q < 32; q++) {
+    const int k1 = brev5(q);
+    plane_p[k1 * 32 + (lane ^ k1)] = x[q];
+  }
+}
+// row reader (thread = row k1 of polynomial pp, register c = column c)
+FB_HD void row_load(double (&x)[32], const double* plane_pp, int k1) {
+#pragma unroll
+  for (int c = 0; c < 32; c++) x[c] = plane_pp[k1 * 32 + (c ^ k1)];
+}
+// inverse inter-pass twiddle in place: register c *= exp(-i*pi*c*(1-4*k1)/2048)
+FB_HD void inv_twiddle_inplace(double (&xr)[32], double (&xi)[32], const c2* tab_i, int k1) {
+  c2 lo[4];
+#pragma unroll
+  for (int l = 0; l < 4; l++) lo[l] = tab_i[l * 32 + k1];
+#pragma unroll
+  for (int h = 0; h < 8; h++) {
+    const c2 hi = tab_i[(4 + h) * 32 + k1];
+#pragma unroll
+    for (int l = 0; l < 4; l++) {
+      const int c = 4 * h + l;
+      double tr = lo[l].x, ti = lo[l].y;
+      if (h != 0) {
+        tr = fb_fma(lo[l].x, hi.x, -(lo[l].y * hi.y));
+        ti = fb_fma(lo[l].x, hi.y, lo[l].y * hi.x);
+      }
+      const double yr = fb_fma(xr[c], tr, -(xi[c] * ti));
+      xi[c] = fb_fma(xr[c], ti, xi[c] * tr);
+      xr[c] = yr;
+    }
+  }
+}
+// row writer (thread = row k1, register c = column c)
+FB_HD void row_store(const double (&x)[32], double* plane_pp, int k1) {
+#pragma unroll
+  for (int c = 0; c < 32; c++) plane_pp[k1 * 32 + (c ^ k1)] = x[c];
+}
+// column reader into the bit-reversed register order fft32_dit_inv wants (register q = row brev5(q))
+FB_HD void col_load_brev(double (&x)[32], const double* plane_p, int lane) {
+#pragma unroll
+  for (int q = 0; q < 32; q++) {
+    const int k1 = brev5(q);
+    x[q] = plane_p[k1 * 32 + (lane ^ k1)];
+  }
+}
+
 // untwist, scale by 1/1024, round to the torus and add into the accumulator polynomial
 FB_HD void phaseC_update(const double (&xr)[32], const double (&xi)[32], uint64_t* accp, int lane) {
 #pragma unroll

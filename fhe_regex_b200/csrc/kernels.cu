@@ -130,44 +130,114 @@ keyswitch_kernel(const uint64_t* __restrict__ ksk, const uint64_t* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2-K4: blind rotation.  S samples per CTA, 2 warps per sample (warp w owns polynomial w in the
-// coefficient-domain phases and rows 16w..16w+15 of both polynomials in the frequency-domain phase).
-// Shared memory per CTA: S * (32 KiB accumulator + 32 KiB transpose buffer) + 12 KiB twiddles
-// + S * 1.5 KiB mod-switched mask.
+// K2-K4: blind rotation.  One CTA per SM: S samples (2 warps each; warp w owns polynomial w in the
+// coefficient-domain phases and rows 16w..16w+15 of both polynomials in the frequency-domain phase)
+// plus one producer warp that streams the Fourier GGSW of CMUX step i (64 KiB, contiguous in HBM/L2)
+// into shared memory with cp.async.bulk (TMA bulk copy) while the samples are still working on
+// step i-1.  All samples of the CTA consume the same staged GGSW; full/empty mbarriers hand the
+// single stage buffer back and forth.
+//
+// Shared memory: 64 KiB GGSW stage + S * (32 KiB u64 accumulator + 16 KiB transpose plane)
+//                + 12 KiB twiddles + S * 1.5 KiB mod-switched mask + 768 B step flags + mbarriers.
 // ------------------------------------------------------------------------------------------------
+constexpr int kGgswBytes = 4 * kHalfN * (int)sizeof(c2);  // 65536
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 template <int S>
-__global__ void __launch_bounds__(64 * S, 1)
+__global__ void __launch_bounds__(64 * S + 32, 1)
 blind_rotate_kernel(const c2* __restrict__ fbsk, const uint64_t* __restrict__ small, const uint64_t* __restrict__ luts,
                     const uint32_t* __restrict__ lut_idx, uint64_t* __restrict__ out, const int32_t* __restrict__ out_rows,
                     const c2* __restrict__ tabs_g, int count) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  uint64_t* acc_all = reinterpret_cast<uint64_t*>(smem);                    // [S][2][2048]
-  c2* tbuf_all = reinterpret_cast<c2*>(smem + (size_t)S * 32768);            // [S][2][1024]
-  c2* tab_f = reinterpret_cast<c2*>(smem + (size_t)S * 65536);               // [12][32]
-  c2* tab_i = tab_f + kTabEntries * 32;                                      // [12][32]
-  uint16_t* at_all = reinterpret_cast<uint16_t*>(tab_i + kTabEntries * 32);  // [S][768]
+  extern __shared__ __align__(128) unsigned char smem[];
+  c2* stage = reinterpret_cast<c2*>(smem);                                             // [2][2][1024]
+  uint64_t* acc_all = reinterpret_cast<uint64_t*>(smem + kGgswBytes);                   // [S][2][2048]
+  double* plane_all = reinterpret_cast<double*>(smem + kGgswBytes + (size_t)S * 32768);  // [S][2][1024]
+  c2* tab_f = reinterpret_cast<c2*>(smem + kGgswBytes + (size_t)S * 49152);              // [12][32]
+  c2* tab_i = tab_f + kTabEntries * 32;                                                 // [12][32]
+  uint16_t* at_all = reinterpret_cast<uint16_t*>(tab_i + kTabEntries * 32);             // [S][768]
+  uint8_t* need = reinterpret_cast<uint8_t*>(at_all + S * 768);                         // [768]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(need + 768);                             // full, empty
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int s = warp >> 1, w = warp & 1;
+  const bool producer = warp == 2 * S;
+  const int s = producer ? 0 : (warp >> 1), w = warp & 1;
   const int sample = blockIdx.x * S + s;
-  const bool active = sample < count;
+  const bool active = !producer && sample < count;
+  const int n_active = min(S, count - (int)blockIdx.x * S);
 
-  for (int t = tid; t < 2 * kTabEntries * 32; t += 64 * S) tab_f[t] = tabs_g[t];
+  for (int t = tid; t < 2 * kTabEntries * 32; t += 64 * S + 32) tab_f[t] = tabs_g[t];
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);                // full: the producer's arrive.expect_tx (+ the bytes)
+    mbar_init(&bars[1], 2 * n_active);     // empty: one arrive per consumer warp
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
   uint16_t* at = at_all + s * 768;
-  if (active) {
-    const uint64_t* sm = small + (size_t)sample * kSmall;
-    for (int t = w * 32 + lane; t < kSmall; t += 64) {
-      const uint64_t x = sm[t];
-      uint32_t a = modswitch(x);
-      if (t < kLweN) a = (a & 4095u) | ((x != 0 && (a & 4095u) != 0) ? 0x8000u : 0u);
+  if (!producer) {
+    for (int t = w * 32 + lane; t < 768; t += 64) {
+      uint32_t a = 0;
+      if (active && t < kSmall) {
+        const uint64_t x = small[(size_t)sample * kSmall + t];
+        a = modswitch(x);
+        if (t < kLweN) a = (a & 4095u) | ((x != 0 && (a & 4095u) != 0) ? 0x8000u : 0u);
+      }
       at[t] = (uint16_t)a;
     }
   }
   __syncthreads();
+  for (int t = tid; t < 768; t += 64 * S + 32) {
+    uint32_t f = 0;
+#pragma unroll
+    for (int ss = 0; ss < S; ss++) f |= at_all[ss * 768 + t];
+    need[t] = (t < kLweN && (f & 0x8000u)) ? 1 : 0;  // some sample of this CTA rotates at step t
+  }
+  __syncthreads();
+
+  if (producer) {
+    if (lane == 0) {
+      uint32_t n_exec = 0;
+      for (int i = 0; i < kLweN; i++) {
+        if (!need[i]) continue;
+        if (n_exec > 0) mbar_wait(&bars[1], (n_exec - 1) & 1u);  // every consumer warp is done with the previous GGSW
+        mbar_arrive_expect_tx(&bars[0], (uint32_t)kGgswBytes);
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(fbsk + (size_t)i * 4 * kHalfN);
+#pragma unroll
+        for (int c = 0; c < 4; c++) bulk_g2s(smem + c * (kGgswBytes / 4), src + c * (kGgswBytes / 4), kGgswBytes / 4, &bars[0]);
+        n_exec++;
+      }
+    }
+    return;
+  }
   if (!active) return;
 
   uint64_t* accp = acc_all + (size_t)s * 2 * kN + (size_t)w * kN;  // polynomial w of this sample
-  c2* tbuf = tbuf_all + (size_t)s * 2 * kHalfN;
+  double* plane = plane_all + (size_t)s * 2 * kHalfN;
   const int bar_id = 1 + s;
 
   // accumulator init: (0, lut * X^{-b})
@@ -180,36 +250,58 @@ blind_rotate_kernel(const c2* __restrict__ fbsk, const uint64_t* __restrict__ sm
 
   double xr[32], xi[32];
   const int pp = lane >> 4, k1 = 16 * w + (lane & 15);
+  const c2* b_own = stage + ((size_t)(pp * 2 + pp) * kHalfN + k1);
+  const c2* b_oth = stage + ((size_t)(pp * 2 + (1 - pp)) * kHalfN + k1);
+  uint32_t n_exec = 0;
   for (int i = 0; i < kLweN; i++) {
+    if (!need[i]) continue;  // CTA-uniform: zero mask element (trivial inputs) or X^0 for every sample
     const uint32_t a = at[i];
-    if (!(a & 0x8000u)) continue;  // warp- and sample-uniform: zero mask element (trivial inputs) or X^0
-    // phase A: this warp's polynomial -> digits -> folded/twisted -> pass 1 -> transpose buffer
+    const uint32_t par = n_exec & 1u;
+    n_exec++;
+    if (!(a & 0x8000u)) {   // this sample skips the step, but still takes part in the hand-over
+      mbar_wait(&bars[0], par);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[1]);
+      continue;
+    }
+    // phase A: this warp's polynomial -> digits -> folded/twisted -> pass 1 -> twiddle -> transpose (re, im)
     phaseA_load(xr, xi, accp, a & 4095u, lane);
     fft32_dif(xr, xi);
-    fwd_twiddle_store(xr, xi, tbuf + w * kHalfN, tab_f, lane);
+    fwd_twiddle_inplace(xr, xi, tab_f, lane);
+    bar_sync(bar_id, 64);                       // previous readers of the plane are done
+    col_store_brev(xr, plane + w * kHalfN, lane);
     bar_sync(bar_id, 64);
-    // phase B: rows -> pass 2 -> Fourier MAC with GGSW_i -> inverse pass 1 -> transpose buffer
-    phaseB_load(xr, xi, tbuf + pp * kHalfN, k1);
+    row_load(xr, plane + pp * kHalfN, k1);
+    bar_sync(bar_id, 64);
+    col_store_brev(xi, plane + w * kHalfN, lane);
+    bar_sync(bar_id, 64);
+    row_load(xi, plane + pp * kHalfN, k1);
+    // phase B: pass 2 -> Fourier MAC with the staged GGSW_i -> inverse pass 1 -> twiddle -> transpose
     fft32_dif(xr, xi);
-    {
-      const c2* b_own = fbsk + fbsk_index(i, pp, pp, k1);
-      const c2* b_oth = fbsk + fbsk_index(i, pp, 1 - pp, k1);
+    mbar_wait(&bars[0], par);
 #pragma unroll
-      for (int q = 0; q < 32; q++) {
-        const int k2 = brev5(q);
-        const c2 bo = __ldg(b_own + 32 * k2);
-        const c2 bx = __ldg(b_oth + 32 * k2);
-        double kr, ki, sr, si;
-        mac_point(xr[q], xi[q], bo, bx, kr, ki, sr, si);
-        xr[q] = kr + __shfl_xor_sync(0xffffffffu, sr, 16);
-        xi[q] = ki + __shfl_xor_sync(0xffffffffu, si, 16);
-      }
+    for (int q = 0; q < 32; q++) {
+      const int k2 = brev5(q);
+      const c2 bo = b_own[32 * k2];
+      const c2 bx = b_oth[32 * k2];
+      double kr, ki, sr, si;
+      mac_point(xr[q], xi[q], bo, bx, kr, ki, sr, si);
+      xr[q] = kr + __shfl_xor_sync(0xffffffffu, sr, 16);
+      xi[q] = ki + __shfl_xor_sync(0xffffffffu, si, 16);
     }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&bars[1]);       // this warp no longer reads the stage
     fft32_dit_inv(xr, xi);
-    inv_twiddle_store(xr, xi, tbuf + pp * kHalfN, tab_i, k1);
+    inv_twiddle_inplace(xr, xi, tab_i, k1);
     bar_sync(bar_id, 64);
-    // phase C: columns -> inverse pass 2 -> untwist, round to torus, accumulate
-    phaseC_load(xr, xi, tbuf + w * kHalfN, lane);
+    row_store(xr, plane + pp * kHalfN, k1);
+    bar_sync(bar_id, 64);
+    col_load_brev(xr, plane + w * kHalfN, lane);
+    bar_sync(bar_id, 64);
+    row_store(xi, plane + pp * kHalfN, k1);
+    bar_sync(bar_id, 64);
+    col_load_brev(xi, plane + w * kHalfN, lane);
+    // phase C: inverse pass 2 -> untwist, round to torus, accumulate
     fft32_dit_inv(xr, xi);
     phaseC_update(xr, xi, accp, lane);
     __syncwarp();
@@ -277,7 +369,9 @@ cudaError_t launch_fp64_peak(double* sink, int ctas, cudaStream_t st) {
 double fp64_peak_flops_per_launch(int ctas) { return (double)ctas * 256.0 * 8.0 * 2.0 * (double)PEAK_ITERS; }
 int br_samples_per_cta() { return 3; }
 
-size_t br_smem_bytes(int S) { return (size_t)S * 65536 + 2 * kTabEntries * 32 * sizeof(c2) + (size_t)S * 768 * sizeof(uint16_t); }
+size_t br_smem_bytes(int S) {
+  return (size_t)kGgswBytes + (size_t)S * 49152 + 2 * kTabEntries * 32 * sizeof(c2) + (size_t)S * 768 * sizeof(uint16_t) + 768 + 16;
+}
 
 cudaError_t launch_bsk_convert(const uint64_t* bsk_std, c2* fbsk, const c2* tabs, cudaStream_t st) {
   const size_t smem = 2 * kHalfN * sizeof(c2) + kTabEntries * 32 * sizeof(c2);
@@ -305,7 +399,7 @@ static cudaError_t launch_br_s(const c2* fbsk, const uint64_t* small, const uint
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  blind_rotate_kernel<S><<<(count + S - 1) / S, 64 * S, smem, st>>>(fbsk, small, luts, lut_idx, out, out_rows, tabs, count);
+  blind_rotate_kernel<S><<<(count + S - 1) / S, 64 * S + 32, smem, st>>>(fbsk, small, luts, lut_idx, out, out_rows, tabs, count);
   return cudaGetLastError();
 }
 

@@ -13,9 +13,9 @@ struct Regs { double xr[32], xi[32]; };
 
 struct Sample {
   std::vector<uint64_t> acc;   // [2][2048]
-  std::vector<c2> tbuf;        // [2][1024]
+  std::vector<double> plane;   // [2][1024]: the re and the im planes pass through it one after the other
   Regs regs[2][32];            // [warp][lane]
-  Sample() : acc(2 * kN), tbuf(2 * kHalfN) {}
+  Sample() : acc(2 * kN), plane(2 * kHalfN) {}
 };
 
 static c2 g_tab_f[kTabEntries * 32], g_tab_i[kTabEntries * 32];
@@ -28,16 +28,40 @@ static void forward_passes(Sample& s) {
     for (int lane = 0; lane < 32; lane++) {
       Regs& R = s.regs[w][lane];
       fft32_dif(R.xr, R.xi);
-      fwd_twiddle_store(R.xr, R.xi, s.tbuf.data() + w * kHalfN, g_tab_f, lane);
+      fwd_twiddle_inplace(R.xr, R.xi, g_tab_f, lane);
     }
-  // barrier
+  // barrier; re plane
+  for (int w = 0; w < 2; w++)
+    for (int lane = 0; lane < 32; lane++) col_store_brev(s.regs[w][lane].xr, s.plane.data() + w * kHalfN, lane);
+  for (int w = 0; w < 2; w++)
+    for (int lane = 0; lane < 32; lane++) row_load(s.regs[w][lane].xr, s.plane.data() + (lane >> 4) * kHalfN, 16 * w + (lane & 15));
+  // barrier; im plane
+  for (int w = 0; w < 2; w++)
+    for (int lane = 0; lane < 32; lane++) col_store_brev(s.regs[w][lane].xi, s.plane.data() + w * kHalfN, lane);
+  for (int w = 0; w < 2; w++)
+    for (int lane = 0; lane < 32; lane++) row_load(s.regs[w][lane].xi, s.plane.data() + (lane >> 4) * kHalfN, 16 * w + (lane & 15));
+  for (int w = 0; w < 2; w++)
+    for (int lane = 0; lane < 32; lane++) fft32_dif(s.regs[w][lane].xr, s.regs[w][lane].xi);
+}
+
+// inverse half: inverse pass 1, twiddle, split transpose, inverse pass 2 (leaves phase-C input in regs)
+static void inverse_passes(Sample& s) {
   for (int w = 0; w < 2; w++)
     for (int lane = 0; lane < 32; lane++) {
       Regs& R = s.regs[w][lane];
-      const int pp = lane >> 4, k1 = 16 * w + (lane & 15);
-      phaseB_load(R.xr, R.xi, s.tbuf.data() + pp * kHalfN, k1);
-      fft32_dif(R.xr, R.xi);
+      fft32_dit_inv(R.xr, R.xi);
+      inv_twiddle_inplace(R.xr, R.xi, g_tab_i, 16 * w + (lane & 15));
     }
+  for (int w = 0; w < 2; w++)
+    for (int lane = 0; lane < 32; lane++) row_store(s.regs[w][lane].xr, s.plane.data() + (lane >> 4) * kHalfN, 16 * w + (lane & 15));
+  for (int w = 0; w < 2; w++)
+    for (int lane = 0; lane < 32; lane++) col_load_brev(s.regs[w][lane].xr, s.plane.data() + w * kHalfN, lane);
+  for (int w = 0; w < 2; w++)
+    for (int lane = 0; lane < 32; lane++) row_store(s.regs[w][lane].xi, s.plane.data() + (lane >> 4) * kHalfN, 16 * w + (lane & 15));
+  for (int w = 0; w < 2; w++)
+    for (int lane = 0; lane < 32; lane++) col_load_brev(s.regs[w][lane].xi, s.plane.data() + w * kHalfN, lane);
+  for (int w = 0; w < 2; w++)
+    for (int lane = 0; lane < 32; lane++) fft32_dit_inv(s.regs[w][lane].xr, s.regs[w][lane].xi);
 }
 
 extern "C" void emu_bsk_to_fourier(const uint64_t* bsk, c2* fbsk) {
@@ -82,20 +106,8 @@ static void cmux_step(Sample& s, const c2* fbsk, int i, uint32_t a) {
         s.regs[w][lane].xi[q] = keep_i[lane] + send_i[lane ^ 16];
       }
     }
-    for (int lane = 0; lane < 32; lane++) {
-      Regs& R = s.regs[w][lane];
-      const int pp = lane >> 4, k1 = 16 * w + (lane & 15);
-      fft32_dit_inv(R.xr, R.xi);
-      inv_twiddle_store(R.xr, R.xi, s.tbuf.data() + pp * kHalfN, g_tab_i, k1);
-    }
   }
-  // barrier
-  for (int w = 0; w < 2; w++)
-    for (int lane = 0; lane < 32; lane++) {
-      Regs& R = s.regs[w][lane];
-      phaseC_load(R.xr, R.xi, s.tbuf.data() + w * kHalfN, lane);
-      fft32_dit_inv(R.xr, R.xi);
-    }
+  inverse_passes(s);
   for (int w = 0; w < 2; w++)
     for (int lane = 0; lane < 32; lane++)
       phaseC_update(s.regs[w][lane].xr, s.regs[w][lane].xi, s.acc.data() + w * kN, lane);
@@ -140,20 +152,16 @@ extern "C" void emu_negacyclic_mul(const int64_t* a_int, const uint64_t* b_torus
   for (int w = 0; w < 2; w++)
     for (int lane = 0; lane < 32; lane++) {
       Regs &A = sa.regs[w][lane], &B = sb.regs[w][lane];
-      const int pp = lane >> 4, k1 = 16 * w + (lane & 15);
       for (int q = 0; q < 32; q++) {
         double r = A.xr[q] * B.xr[q] - A.xi[q] * B.xi[q], im = A.xr[q] * B.xi[q] + A.xi[q] * B.xr[q];
         A.xr[q] = r; A.xi[q] = im;
       }
-      fft32_dit_inv(A.xr, A.xi);
-      inv_twiddle_store(A.xr, A.xi, sa.tbuf.data() + pp * kHalfN, g_tab_i, k1);
     }
+  inverse_passes(sa);
   std::fill(sa.acc.begin(), sa.acc.end(), 0);
   for (int w = 0; w < 2; w++)
     for (int lane = 0; lane < 32; lane++) {
       Regs& R = sa.regs[w][lane];
-      phaseC_load(R.xr, R.xi, sa.tbuf.data() + w * kHalfN, lane);
-      fft32_dit_inv(R.xr, R.xi);
       phaseC_update(R.xr, R.xi, sa.acc.data() + w * kN, lane);
     }
   memcpy(out, sa.acc.data(), sizeof(uint64_t) * kN);
