@@ -108,6 +108,59 @@ FB_HD void phaseA_load(double (&xr)[32], double (&xi)[32], const uint64_t* accp,
   }
 }
 
+// ---- 32-bit shadow accumulator ---------------------------------------------------------------
+// The 64-bit accumulator of a sample lives thread-privately (tensor memory on the device); shared
+// memory only holds a 32-bit shadow -- the top word of every coefficient, rounded -- which is all the
+// decomposition of acc*X^a - acc needs: the digit keeps 23 bits, so a 32-bit difference moves the
+// closest-representable rounding point by at most 2^-32 (the f64 FFT error is ~2^-15).
+FB_HD uint32_t shadow_word(uint64_t a) { return (uint32_t)((a + 0x80000000ull) >> 32); }
+
+FB_HD uint32_t rot_read32(const uint32_t* shp, uint32_t j, uint32_t a) {
+  const uint32_t idx = (j - a) & 4095u;
+  const uint32_t v = shp[idx & 2047u];
+  return (idx & 2048u) ? 0u - v : v;
+}
+
+// balanced base-2^23 digit of a 32-bit torus difference: round(diff / 2^9) in [-2^22, 2^22]
+FB_HD double pbs_digit32(uint32_t diff) {
+  const int32_t d = (int32_t)(diff + 256u) >> 9;
+  return (double)d;
+}
+
+FB_HD void phaseA_load32(double (&xr)[32], double (&xi)[32], const uint32_t* shp, uint32_t a, int lane) {
+#pragma unroll
+  for (int r = 0; r < 32; r++) {
+    const uint32_t j = 32u * r + lane;
+    const double d0 = pbs_digit32(rot_read32(shp, j, a) - shp[j]);
+    const double d1 = pbs_digit32(rot_read32(shp, j + 1024u, a) - shp[j + 1024u]);
+    const double cr = fb_twist_cos(r), sr = fb_twist_sin(r);
+    xr[r] = fb_fma(d0, cr, -(d1 * sr));
+    xi[r] = fb_fma(d0, sr, d1 * cr);
+  }
+}
+
+// phase C for one register: torus increments of coefficients 32r+lane (re) and 32r+lane+1024 (im)
+FB_HD void phaseC_increments(const double (&xr)[32], const double (&xi)[32], int r, uint64_t& inc0, uint64_t& inc1) {
+  const double cr = fb_twist_cos(r) * (1.0 / 1024.0), sr = fb_twist_sin(r) * (1.0 / 1024.0);
+  inc0 = from_torus(fb_fma(xr[r], cr, xi[r] * sr));
+  inc1 = from_torus(fb_fma(xi[r], cr, -(xr[r] * sr)));
+}
+
+// Fourier MAC of one frequency point: out = x * b_own + partner * b_in, where `partner` is the other
+// polynomial's spectrum value at the same frequency (lane ^ 16) and b_in = GGSW[other row][my column]
+FB_HD void mac_point2(double& xr, double& xi, double pr, double pi, c2 b_own, c2 b_in) {
+  double orr = xr * b_own.x;
+  orr = fb_fma(-xi, b_own.y, orr);
+  orr = fb_fma(pr, b_in.x, orr);
+  orr = fb_fma(-pi, b_in.y, orr);
+  double oi = xr * b_own.y;
+  oi = fb_fma(xi, b_own.x, oi);
+  oi = fb_fma(pr, b_in.y, oi);
+  oi = fb_fma(pi, b_in.x, oi);
+  xr = orr;
+  xi = oi;
+}
+
 // same folding for a standard-domain key polynomial read as a signed torus value in [-1/2, 1/2)
 // (key conversion K7; tfhe-rs forward_as_torus)
 FB_HD void phaseA_load_torus(double (&xr)[32], double (&xi)[32], const uint64_t* poly, int lane) {

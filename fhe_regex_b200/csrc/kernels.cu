@@ -130,15 +130,18 @@ keyswitch_kernel(const uint64_t* __restrict__ ksk, const uint64_t* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2-K4: blind rotation.  One CTA per SM: S samples (2 warps each; warp w owns polynomial w in the
-// coefficient-domain phases and rows 16w..16w+15 of both polynomials in the frequency-domain phase)
-// plus one producer warp that streams the Fourier GGSW of CMUX step i (64 KiB, contiguous in HBM/L2)
-// into shared memory with cp.async.bulk (TMA bulk copy) while the samples are still working on
-// step i-1.  All samples of the CTA consume the same staged GGSW; full/empty mbarriers hand the
-// single stage buffer back and forth.
+// K2-K4: blind rotation.  One CTA per SM: S samples, 2 warps each (warp w owns polynomial w in the
+// coefficient-domain phases and rows 16w..16w+15 of both polynomials in the frequency-domain phase).
+// The Fourier GGSW of CMUX step i (64 KiB, contiguous in HBM/L2) is streamed into one shared-memory
+// stage with cp.async.bulk (TMA bulk copy) and consumed by all samples of the CTA; the warp that is
+// last to finish its Fourier MAC of step i (shared-memory arrival counter) issues the copy of step
+// i+1, which lands while the samples run their inverse transforms and the next forward transforms;
+// an mbarrier with a transaction count tells the consumers when the bytes are there.
+// The 64-bit accumulators live thread-privately in tensor memory (TMEM, tcgen05.ld/st); shared memory
+// holds only a 32-bit shadow for the rotation reads of the decomposition.
 //
-// Shared memory: 64 KiB GGSW stage + S * (32 KiB u64 accumulator + 16 KiB transpose plane)
-//                + 12 KiB twiddles + S * 1.5 KiB mod-switched mask + 768 B step flags + mbarriers.
+// Shared memory: 64 KiB GGSW stage + S * (16 KiB u32 shadow accumulator + 16 KiB transpose plane)
+//                + 12 KiB twiddles + S * 1.5 KiB mod-switched mask + 768 B step flags + mbarrier.
 // ------------------------------------------------------------------------------------------------
 constexpr int kGgswBytes = 4 * kHalfN * (int)sizeof(c2);  // 65536
 
@@ -169,37 +172,76 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                : "memory");
 }
 
+// ---- tensor memory (TMEM) as thread-private storage of the 64-bit accumulators ----------------------
+// TMEM is 128 lanes x 512 32-bit columns per SM; warp w of a CTA may touch lanes 32*(w%4) .. +31 only, and
+// tcgen05.ld/st.32x32b hands thread `lane` consecutive columns of its own lane: exactly a 256 KiB
+// register-file extension.  Each consumer warp owns 128 columns (64 u64 coefficients per thread).
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+  // the registers are valid only after the wait; tying them to it keeps the compiler from using them earlier
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                 "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+constexpr int kTmemCols = 512;
+
 template <int S>
-__global__ void __launch_bounds__(64 * S + 32, 1)
+__global__ void __launch_bounds__(64 * S, 1)
 blind_rotate_kernel(const c2* __restrict__ fbsk, const uint64_t* __restrict__ small, const uint64_t* __restrict__ luts,
                     const uint32_t* __restrict__ lut_idx, uint64_t* __restrict__ out, const int32_t* __restrict__ out_rows,
                     const c2* __restrict__ tabs_g, int count) {
+  static_assert(2 * S <= 16, "128 TMEM columns per consumer warp, 4 warps per lane quarter");
   extern __shared__ __align__(128) unsigned char smem[];
   c2* stage = reinterpret_cast<c2*>(smem);                                             // [2][2][1024]
-  uint64_t* acc_all = reinterpret_cast<uint64_t*>(smem + kGgswBytes);                   // [S][2][2048]
-  double* plane_all = reinterpret_cast<double*>(smem + kGgswBytes + (size_t)S * 32768);  // [S][2][1024]
-  c2* tab_f = reinterpret_cast<c2*>(smem + kGgswBytes + (size_t)S * 49152);              // [12][32]
+  uint32_t* shadow_all = reinterpret_cast<uint32_t*>(smem + kGgswBytes);                // [S][2][2048]
+  double* plane_all = reinterpret_cast<double*>(smem + kGgswBytes + (size_t)S * 16384);  // [S][2][1024]
+  c2* tab_f = reinterpret_cast<c2*>(smem + kGgswBytes + (size_t)S * 32768);              // [12][32]
   c2* tab_i = tab_f + kTabEntries * 32;                                                 // [12][32]
   uint16_t* at_all = reinterpret_cast<uint16_t*>(tab_i + kTabEntries * 32);             // [S][768]
   uint8_t* need = reinterpret_cast<uint8_t*>(at_all + S * 768);                         // [768]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(need + 768);                             // full, empty
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(need + 768);                         // GGSW bytes have landed
+  uint32_t* done_cnt = reinterpret_cast<uint32_t*>(full_bar + 1);                       // warps done with the stage
+  uint32_t* tmem_slot = done_cnt + 1;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool producer = warp == 2 * S;
-  const int s = producer ? 0 : (warp >> 1), w = warp & 1;
+  const int s = warp >> 1, w = warp & 1;
   const int sample = blockIdx.x * S + s;
-  const bool active = !producer && sample < count;
-  const int n_active = min(S, count - (int)blockIdx.x * S);
+  const bool active = sample < count;
+  const uint32_t n_warps_active = 2u * (uint32_t)min(S, count - (int)blockIdx.x * S);
 
-  for (int t = tid; t < 2 * kTabEntries * 32; t += 64 * S + 32) tab_f[t] = tabs_g[t];
+  for (int t = tid; t < 2 * kTabEntries * 32; t += 64 * S) tab_f[t] = tabs_g[t];
   if (tid == 0) {
-    mbar_init(&bars[0], 1);                // full: the producer's arrive.expect_tx (+ the bytes)
-    mbar_init(&bars[1], 2 * n_active);     // empty: one arrive per consumer warp
+    mbar_init(full_bar, 1);                // one arrive.expect_tx per staged GGSW (+ its bytes)
+    *done_cnt = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
+  if (warp == 0) tmem_alloc(tmem_slot, kTmemCols);
   uint16_t* at = at_all + s * 768;
-  if (!producer) {
+  {
     for (int t = w * 32 + lane; t < 768; t += 64) {
       uint32_t a = 0;
       if (active && t < kSmall) {
@@ -210,8 +252,11 @@ blind_rotate_kernel(const c2* __restrict__ fbsk, const uint64_t* __restrict__ sm
       at[t] = (uint16_t)a;
     }
   }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  for (int t = tid; t < 768; t += 64 * S + 32) {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  for (int t = tid; t < 768; t += 64 * S) {
     uint32_t f = 0;
 #pragma unroll
     for (int ss = 0; ss < S; ss++) f |= at_all[ss * 768 + t];
@@ -219,104 +264,161 @@ blind_rotate_kernel(const c2* __restrict__ fbsk, const uint64_t* __restrict__ sm
   }
   __syncthreads();
 
-  if (producer) {
-    if (lane == 0) {
-      uint32_t n_exec = 0;
-      for (int i = 0; i < kLweN; i++) {
-        if (!need[i]) continue;
-        if (n_exec > 0) mbar_wait(&bars[1], (n_exec - 1) & 1u);  // every consumer warp is done with the previous GGSW
-        mbar_arrive_expect_tx(&bars[0], (uint32_t)kGgswBytes);
-        const unsigned char* src = reinterpret_cast<const unsigned char*>(fbsk + (size_t)i * 4 * kHalfN);
+  // stage hand-over: issue the bulk copy of the GGSW of step i (called by exactly one thread)
+  auto issue_ggsw = [&](int i) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_arrive_expect_tx(full_bar, (uint32_t)kGgswBytes);
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(fbsk + (size_t)i * 4 * kHalfN);
 #pragma unroll
-        for (int c = 0; c < 4; c++) bulk_g2s(smem + c * (kGgswBytes / 4), src + c * (kGgswBytes / 4), kGgswBytes / 4, &bars[0]);
-        n_exec++;
+    for (int c = 0; c < 4; c++) bulk_g2s(smem + c * (kGgswBytes / 4), src + c * (kGgswBytes / 4), kGgswBytes / 4, full_bar);
+  };
+  // a warp is done reading the stage for step i; the last one to say so starts the copy of the next needed step
+  auto release_stage = [&](int i) {
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence_block();
+      if (atomicAdd(done_cnt, 1u) == n_warps_active - 1u) {
+        *reinterpret_cast<volatile uint32_t*>(done_cnt) = 0u;
+        int j = i + 1;
+        while (j < kLweN && !need[j]) j++;
+        if (j < kLweN) issue_ggsw(j);
       }
     }
-    return;
+  };
+  if (tid == 0) {
+    int j = 0;
+    while (j < kLweN && !need[j]) j++;
+    if (j < kLweN) issue_ggsw(j);
   }
-  if (!active) return;
 
-  uint64_t* accp = acc_all + (size_t)s * 2 * kN + (size_t)w * kN;  // polynomial w of this sample
-  double* plane = plane_all + (size_t)s * 2 * kHalfN;
-  const int bar_id = 1 + s;
+  if (active) {
+    uint32_t* shp = shadow_all + (size_t)s * 2 * kN + (size_t)w * kN;  // shadow of polynomial w of this sample
+    double* plane = plane_all + (size_t)s * 2 * kHalfN;
+    const int bar_id = 1 + s;
+    // this warp's 128 TMEM columns: coefficient 32r+lane in columns 4r,4r+1 (lo,hi), 32r+lane+1024 in 4r+2,4r+3
+    const uint32_t tacc = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 128);
 
-  // accumulator init: (0, lut * X^{-b})
-  {
-    const uint64_t* lut = luts + (size_t)lut_idx[sample] * kN;
-    const uint32_t rot = (4096u - (uint32_t)at[kLweN]) & 4095u;
-    for (int j = lane; j < kN; j += 32) accp[j] = (w == 0) ? 0ull : rot_read(lut, (uint32_t)j, rot);
-  }
-  __syncwarp();
-
-  double xr[32], xi[32];
-  const int pp = lane >> 4, k1 = 16 * w + (lane & 15);
-  const c2* b_own = stage + ((size_t)(pp * 2 + pp) * kHalfN + k1);
-  const c2* b_oth = stage + ((size_t)(pp * 2 + (1 - pp)) * kHalfN + k1);
-  uint32_t n_exec = 0;
-  for (int i = 0; i < kLweN; i++) {
-    if (!need[i]) continue;  // CTA-uniform: zero mask element (trivial inputs) or X^0 for every sample
-    const uint32_t a = at[i];
-    const uint32_t par = n_exec & 1u;
-    n_exec++;
-    if (!(a & 0x8000u)) {   // this sample skips the step, but still takes part in the hand-over
-      mbar_wait(&bars[0], par);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars[1]);
-      continue;
-    }
-    // phase A: this warp's polynomial -> digits -> folded/twisted -> pass 1 -> twiddle -> transpose (re, im)
-    phaseA_load(xr, xi, accp, a & 4095u, lane);
-    fft32_dif(xr, xi);
-    fwd_twiddle_inplace(xr, xi, tab_f, lane);
-    bar_sync(bar_id, 64);                       // previous readers of the plane are done
-    col_store_brev(xr, plane + w * kHalfN, lane);
-    bar_sync(bar_id, 64);
-    row_load(xr, plane + pp * kHalfN, k1);
-    bar_sync(bar_id, 64);
-    col_store_brev(xi, plane + w * kHalfN, lane);
-    bar_sync(bar_id, 64);
-    row_load(xi, plane + pp * kHalfN, k1);
-    // phase B: pass 2 -> Fourier MAC with the staged GGSW_i -> inverse pass 1 -> twiddle -> transpose
-    fft32_dif(xr, xi);
-    mbar_wait(&bars[0], par);
+    // accumulator init: (0, lut * X^{-b})
+    {
+      const uint64_t* lut = luts + (size_t)lut_idx[sample] * kN;
+      const uint32_t rot = (4096u - (uint32_t)at[kLweN]) & 4095u;
+#pragma unroll 1
+      for (int g = 0; g < 8; g++) {
+        uint32_t v[16];
 #pragma unroll
-    for (int q = 0; q < 32; q++) {
-      const int k2 = brev5(q);
-      const c2 bo = b_own[32 * k2];
-      const c2 bx = b_oth[32 * k2];
-      double kr, ki, sr, si;
-      mac_point(xr[q], xi[q], bo, bx, kr, ki, sr, si);
-      xr[q] = kr + __shfl_xor_sync(0xffffffffu, sr, 16);
-      xi[q] = ki + __shfl_xor_sync(0xffffffffu, si, 16);
+        for (int t = 0; t < 4; t++) {
+          const uint32_t j = 32u * (4 * g + t) + lane;
+          const uint64_t a0 = (w == 0) ? 0ull : rot_read(lut, j, rot);
+          const uint64_t a1 = (w == 0) ? 0ull : rot_read(lut, j + 1024u, rot);
+          v[4 * t] = (uint32_t)a0; v[4 * t + 1] = (uint32_t)(a0 >> 32);
+          v[4 * t + 2] = (uint32_t)a1; v[4 * t + 3] = (uint32_t)(a1 >> 32);
+          shp[j] = shadow_word(a0);
+          shp[j + 1024u] = shadow_word(a1);
+        }
+        tmem_st16(tacc + 16 * g, v);
+      }
+      tmem_wait_st();
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&bars[1]);       // this warp no longer reads the stage
-    fft32_dit_inv(xr, xi);
-    inv_twiddle_inplace(xr, xi, tab_i, k1);
-    bar_sync(bar_id, 64);
-    row_store(xr, plane + pp * kHalfN, k1);
-    bar_sync(bar_id, 64);
-    col_load_brev(xr, plane + w * kHalfN, lane);
-    bar_sync(bar_id, 64);
-    row_store(xi, plane + pp * kHalfN, k1);
-    bar_sync(bar_id, 64);
-    col_load_brev(xi, plane + w * kHalfN, lane);
-    // phase C: inverse pass 2 -> untwist, round to torus, accumulate
-    fft32_dit_inv(xr, xi);
-    phaseC_update(xr, xi, accp, lane);
-    __syncwarp();
-  }
 
-  // K4: sample extract of the constant coefficient
-  bar_sync(bar_id, 64);
-  {
-    const uint64_t* am = acc_all + (size_t)s * 2 * kN;
-    const uint64_t* ab = am + kN;
-    const size_t row = out_rows ? (size_t)out_rows[sample] : (size_t)sample;
-    uint64_t* o = out + row * kBig;
-    for (int j = w * 32 + lane; j < kN; j += 64) o[j] = (j == 0) ? am[0] : (uint64_t)0 - am[kN - j];
-    if (w == 0 && lane == 0) o[kN] = ab[0];
+    double xr[32], xi[32];
+    const int pp = lane >> 4, k1 = 16 * w + (lane & 15);
+    const c2* b_own = stage + ((size_t)(pp * 2 + pp) * kHalfN + k1);        // GGSW[row pp][column pp]
+    const c2* b_in = stage + ((size_t)((1 - pp) * 2 + pp) * kHalfN + k1);   // GGSW[row 1-pp][column pp]
+    uint32_t n_exec = 0;
+    for (int i = 0; i < kLweN; i++) {
+      if (!need[i]) continue;  // CTA-uniform: zero mask element (trivial inputs) or X^0 for every sample
+      const uint32_t a = at[i];
+      const uint32_t par = n_exec & 1u;
+      n_exec++;
+      if (!(a & 0x8000u)) {   // this sample skips the step, but still takes part in the hand-over
+        mbar_wait(full_bar, par);
+        release_stage(i);
+        continue;
+      }
+      // phase A: this warp's polynomial -> digits -> folded/twisted -> pass 1 -> twiddle -> transpose (re, im)
+      phaseA_load32(xr, xi, shp, a & 4095u, lane);
+      fft32_dif(xr, xi);
+      fwd_twiddle_inplace(xr, xi, tab_f, lane);
+      bar_sync(bar_id, 64);                       // previous readers of the plane are done
+      col_store_brev(xr, plane + w * kHalfN, lane);
+      bar_sync(bar_id, 64);
+      row_load(xr, plane + pp * kHalfN, k1);
+      bar_sync(bar_id, 64);
+      col_store_brev(xi, plane + w * kHalfN, lane);
+      bar_sync(bar_id, 64);
+      row_load(xi, plane + pp * kHalfN, k1);
+      // phase B: pass 2 -> Fourier MAC with the staged GGSW_i -> inverse pass 1 -> twiddle -> transpose
+      fft32_dif(xr, xi);
+      mbar_wait(full_bar, par);
+#pragma unroll
+      for (int q = 0; q < 32; q++) {
+        const int k2 = brev5(q);
+        const double pr = __shfl_xor_sync(0xffffffffu, xr[q], 16);
+        const double pi = __shfl_xor_sync(0xffffffffu, xi[q], 16);
+        mac_point2(xr[q], xi[q], pr, pi, b_own[32 * k2], b_in[32 * k2]);
+      }
+      release_stage(i);                           // this warp no longer reads the stage
+      fft32_dit_inv(xr, xi);
+      inv_twiddle_inplace(xr, xi, tab_i, k1);
+      bar_sync(bar_id, 64);
+      row_store(xr, plane + pp * kHalfN, k1);
+      bar_sync(bar_id, 64);
+      col_load_brev(xr, plane + w * kHalfN, lane);
+      bar_sync(bar_id, 64);
+      row_store(xi, plane + pp * kHalfN, k1);
+      bar_sync(bar_id, 64);
+      col_load_brev(xi, plane + w * kHalfN, lane);
+      // phase C: inverse pass 2 -> untwist, round to torus, accumulate into TMEM, refresh the shadow
+      fft32_dit_inv(xr, xi);
+#pragma unroll
+      for (int g = 0; g < 8; g++) {
+        uint32_t v[16];
+        tmem_ld16(tacc + 16 * g, v);
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+          const int r = 4 * g + t;
+          uint64_t inc0, inc1;
+          phaseC_increments(xr, xi, r, inc0, inc1);
+          const uint64_t a0 = (((uint64_t)v[4 * t + 1] << 32) | v[4 * t]) + inc0;
+          const uint64_t a1 = (((uint64_t)v[4 * t + 3] << 32) | v[4 * t + 2]) + inc1;
+          v[4 * t] = (uint32_t)a0; v[4 * t + 1] = (uint32_t)(a0 >> 32);
+          v[4 * t + 2] = (uint32_t)a1; v[4 * t + 3] = (uint32_t)(a1 >> 32);
+          shp[32 * r + lane] = shadow_word(a0);
+          shp[32 * r + lane + 1024] = shadow_word(a1);
+        }
+        tmem_st16(tacc + 16 * g, v);
+      }
+      tmem_wait_st();
+      __syncwarp();
+    }
+
+    // K4: sample extract of the constant coefficient: mask_0 = a_0, mask_j = -a_{N-j}; body = b_0
+    {
+      const size_t row = out_rows ? (size_t)out_rows[sample] : (size_t)sample;
+      uint64_t* o = out + row * kBig;
+#pragma unroll 1
+      for (int g = 0; g < 8; g++) {
+        uint32_t v[16];
+        tmem_ld16(tacc + 16 * g, v);
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+          const uint32_t j = 32u * (4 * g + t) + lane;
+          const uint64_t a0 = ((uint64_t)v[4 * t + 1] << 32) | v[4 * t];
+          const uint64_t a1 = ((uint64_t)v[4 * t + 3] << 32) | v[4 * t + 2];
+          if (w == 0) {
+            if (j == 0) o[0] = a0; else o[kN - j] = (uint64_t)0 - a0;
+            o[kN - (j + 1024u)] = (uint64_t)0 - a1;
+          } else if (j == 0) {
+            o[kN] = a0;
+          }
+        }
+      }
+    }
   }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -367,10 +469,10 @@ cudaError_t launch_fp64_peak(double* sink, int ctas, cudaStream_t st) {
   return cudaGetLastError();
 }
 double fp64_peak_flops_per_launch(int ctas) { return (double)ctas * 256.0 * 8.0 * 2.0 * (double)PEAK_ITERS; }
-int br_samples_per_cta() { return 3; }
+int br_samples_per_cta() { return 4; }
 
 size_t br_smem_bytes(int S) {
-  return (size_t)kGgswBytes + (size_t)S * 49152 + 2 * kTabEntries * 32 * sizeof(c2) + (size_t)S * 768 * sizeof(uint16_t) + 768 + 16;
+  return (size_t)kGgswBytes + (size_t)S * 32768 + 2 * kTabEntries * 32 * sizeof(c2) + (size_t)S * 768 * sizeof(uint16_t) + 768 + 16 + 16;
 }
 
 cudaError_t launch_bsk_convert(const uint64_t* bsk_std, c2* fbsk, const c2* tabs, cudaStream_t st) {
@@ -399,14 +501,14 @@ static cudaError_t launch_br_s(const c2* fbsk, const uint64_t* small, const uint
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  blind_rotate_kernel<S><<<(count + S - 1) / S, 64 * S + 32, smem, st>>>(fbsk, small, luts, lut_idx, out, out_rows, tabs, count);
+  blind_rotate_kernel<S><<<(count + S - 1) / S, 64 * S, smem, st>>>(fbsk, small, luts, lut_idx, out, out_rows, tabs, count);
   return cudaGetLastError();
 }
 
 cudaError_t launch_blind_rotate(const c2* fbsk, const uint64_t* small, const uint64_t* luts, const uint32_t* lut_idx,
                                 uint64_t* out, const int32_t* out_rows, const c2* tabs, int count, cudaStream_t st) {
   if (count <= 0) return cudaSuccess;
-  return launch_br_s<3>(fbsk, small, luts, lut_idx, out, out_rows, tabs, count, st);
+  return launch_br_s<4>(fbsk, small, luts, lut_idx, out, out_rows, tabs, count, st);
 }
 
 cudaError_t launch_lincomb(uint64_t* arena, const int32_t* out_rows, const int32_t* term_off, const int32_t* term_rows,

@@ -12,10 +12,12 @@ using namespace fb;
 struct Regs { double xr[32], xi[32]; };
 
 struct Sample {
-  std::vector<uint64_t> acc;   // [2][2048]
+  std::vector<uint64_t> acc;   // [2][2048] (only used by the product check)
+  std::vector<uint32_t> shadow; // [2][2048] 32-bit shadow accumulator (shared memory on the device)
+  uint64_t master[2][32][64];  // [warp][lane][2r + half]: thread-private 64-bit accumulator (tensor memory on the device)
   std::vector<double> plane;   // [2][1024]: the re and the im planes pass through it one after the other
   Regs regs[2][32];            // [warp][lane]
-  Sample() : acc(2 * kN), plane(2 * kHalfN) {}
+  Sample() : acc(2 * kN), shadow(2 * kN), plane(2 * kHalfN) {}
 };
 
 static c2 g_tab_f[kTabEntries * 32], g_tab_i[kTabEntries * 32];
@@ -88,46 +90,61 @@ extern "C" void emu_bsk_to_fourier(const uint64_t* bsk, c2* fbsk) {
 static void cmux_step(Sample& s, const c2* fbsk, int i, uint32_t a) {
   for (int w = 0; w < 2; w++)
     for (int lane = 0; lane < 32; lane++)
-      phaseA_load(s.regs[w][lane].xr, s.regs[w][lane].xi, s.acc.data() + w * kN, a, lane);
+      phaseA_load32(s.regs[w][lane].xr, s.regs[w][lane].xi, s.shadow.data() + w * kN, a, lane);
   forward_passes(s);
-  // MAC with the shuffle exchange between lane and lane^16
+  // MAC: every lane takes the other polynomial's spectrum value from lane ^ 16
   for (int w = 0; w < 2; w++) {
     for (int q = 0; q < 32; q++) {
-      double keep_r[32], keep_i[32], send_r[32], send_i[32];
+      double pr[32], pi[32];
+      for (int lane = 0; lane < 32; lane++) { pr[lane] = s.regs[w][lane ^ 16].xr[q]; pi[lane] = s.regs[w][lane ^ 16].xi[q]; }
       for (int lane = 0; lane < 32; lane++) {
         Regs& R = s.regs[w][lane];
         const int pp = lane >> 4, k1 = 16 * w + (lane & 15);
         const int k = k1 + 32 * brev5(q);
-        mac_point(R.xr[q], R.xi[q], fbsk[fbsk_index(i, pp, pp, k)], fbsk[fbsk_index(i, pp, 1 - pp, k)],
-                  keep_r[lane], keep_i[lane], send_r[lane], send_i[lane]);
-      }
-      for (int lane = 0; lane < 32; lane++) {
-        s.regs[w][lane].xr[q] = keep_r[lane] + send_r[lane ^ 16];
-        s.regs[w][lane].xi[q] = keep_i[lane] + send_i[lane ^ 16];
+        mac_point2(R.xr[q], R.xi[q], pr[lane], pi[lane], fbsk[fbsk_index(i, pp, pp, k)], fbsk[fbsk_index(i, 1 - pp, pp, k)]);
       }
     }
   }
   inverse_passes(s);
   for (int w = 0; w < 2; w++)
     for (int lane = 0; lane < 32; lane++)
-      phaseC_update(s.regs[w][lane].xr, s.regs[w][lane].xi, s.acc.data() + w * kN, lane);
+      for (int r = 0; r < 32; r++) {
+        uint64_t inc0, inc1;
+        phaseC_increments(s.regs[w][lane].xr, s.regs[w][lane].xi, r, inc0, inc1);
+        uint64_t& a0 = s.master[w][lane][2 * r];
+        uint64_t& a1 = s.master[w][lane][2 * r + 1];
+        a0 += inc0;
+        a1 += inc1;
+        s.shadow[w * kN + 32 * r + lane] = shadow_word(a0);
+        s.shadow[w * kN + 32 * r + lane + 1024] = shadow_word(a1);
+      }
 }
 
 // small[743], lut[2048] -> acc[2][2048]; max_steps < 0 means all 742
 extern "C" void emu_blind_rotate(const c2* fbsk, const uint64_t* small, const uint64_t* lut, uint64_t* acc_out, int max_steps) {
   tabs();
-  Sample s;
+  Sample& s = *new Sample();
   const uint32_t bt = modswitch(small[kLweN]);
-  for (int j = 0; j < kN; j++) {
-    s.acc[j] = 0;
-    s.acc[kN + j] = rot_read(lut, j, (4096u - bt) & 4095u);
-  }
+  for (int w = 0; w < 2; w++)
+    for (int lane = 0; lane < 32; lane++)
+      for (int r = 0; r < 32; r++)
+        for (int h = 0; h < 2; h++) {
+          const int j = 32 * r + lane + 1024 * h;
+          const uint64_t v = w == 0 ? 0ull : rot_read(lut, j, (4096u - bt) & 4095u);
+          s.master[w][lane][2 * r + h] = v;
+          s.shadow[w * kN + j] = shadow_word(v);
+        }
   const int steps = max_steps < 0 ? kLweN : max_steps;
   for (int i = 0; i < steps; i++) {
-    if (small[i] == 0) continue;
-    cmux_step(s, fbsk, i, modswitch(small[i]) & 4095u);
+    const uint32_t a = modswitch(small[i]) & 4095u;
+    if (small[i] == 0 || a == 0) continue;
+    cmux_step(s, fbsk, i, a);
   }
-  memcpy(acc_out, s.acc.data(), sizeof(uint64_t) * 2 * kN);
+  for (int w = 0; w < 2; w++)
+    for (int lane = 0; lane < 32; lane++)
+      for (int r = 0; r < 32; r++)
+        for (int h = 0; h < 2; h++) acc_out[w * kN + 32 * r + lane + 1024 * h] = s.master[w][lane][2 * r + h];
+  delete &s;
 }
 
 // negacyclic product check: out = round(a_int (*) b_torus) using forward/pointwise/inverse of the emulated passes

@@ -1,0 +1,79 @@
+"""CPU lane-by-lane emulation of the blind-rotation kernel's data flow (tests/emu/emu_br.cpp, built from
+the same __host__ __device__ phase functions the CUDA kernel uses) against the oracle.  Lets the index /
+twiddle / swizzle / accumulator-layout logic be checked in the build container, which has no GPU."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import tfhe
+
+EMU_DIR = os.path.join(os.path.dirname(__file__), "emu")
+CSRC = os.path.join(os.path.dirname(EMU_DIR), "..", "fhe_regex_b200", "csrc")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    so = os.path.join(EMU_DIR, "libemu_br.so")
+    srcs = [os.path.join(EMU_DIR, "emu_br.cpp"), os.path.join(CSRC, "br_core.cuh"), os.path.join(CSRC, "fft32_gen.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(s) for s in srcs):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-march=x86-64-v3", "-fPIC", "-shared", "-o", so, srcs[0]])
+    return ctypes.CDLL(so)
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+@pytest.fixture(scope="module")
+def emu_fbsk(emu, server_key):
+    out = np.zeros((742, 2, 2, 1024, 2), dtype=np.float64)
+    emu.emu_bsk_to_fourier(_p(server_key.bsk), _p(out))
+    return out
+
+
+def test_emulated_negacyclic_product_matches_exact(emu):
+    rng = np.random.default_rng(3)
+    a = rng.integers(-(1 << 22), 1 << 22, size=2048, dtype=np.int64)
+    b = rng.integers(0, 1 << 64, size=2048, dtype=np.uint64)
+    got = np.zeros(2048, dtype=np.uint64)
+    emu.emu_negacyclic_mul(_p(a), _p(b), _p(got))
+    # exact negacyclic product mod 2^64 with python ints on a few coefficients
+    ai, bi = [int(x) for x in a], [int(x) for x in b]
+    for j in (0, 1, 7, 1023, 1024, 2047):
+        s = 0
+        for t in range(2048):
+            u = j - t
+            s += ai[t] * bi[u] if u >= 0 else -ai[t] * bi[u + 2048]
+        err = tfhe.torus_err(np.array([got[j]], dtype=np.uint64), np.array([s % (1 << 64)], dtype=np.uint64))[0]
+        assert abs(err) < 2 ** -20, (j, err)
+
+
+def test_emulated_blind_rotate_decrypts_like_the_oracle(emu, emu_fbsk, client_key, server_key):
+    msgs = np.array([3, 12], dtype=np.int64)
+    cts = tfhe.encrypt_batch(client_key, msgs, seed=77)
+    small = tfhe.keyswitch(server_key, cts)
+    lut = tfhe.make_lut(lambda x: (x * 3 + 1) % 16)
+    for b in range(len(msgs)):
+        acc = np.zeros(2 * 2048, dtype=np.uint64)
+        emu.emu_blind_rotate(_p(emu_fbsk), _p(small[b]), _p(lut), _p(acc), -1)
+        out = tfhe.sample_extract(acc)
+        exp = (int(msgs[b]) * 3 + 1) % 16
+        assert tfhe.decrypt_shortint(client_key, out) == exp
+        ref = tfhe.bootstrap_small(server_key, small[b], lut)
+        assert tfhe.decrypt_shortint(client_key, ref) == exp
+        ph = tfhe.phase_batch(client_key.big, np.stack([out, ref]))
+        err = tfhe.torus_err(ph, np.array([exp << 59] * 2, dtype=np.uint64))
+        assert np.abs(err).max() < 4e-4, err
+
+
+def test_emulated_trivial_input_is_exact(emu, emu_fbsk, server_key):
+    lut = tfhe.make_lut(lambda x: (5 * x) % 16)
+    small = np.zeros(743, dtype=np.uint64)
+    small[742] = np.uint64(9 << 59)
+    acc = np.zeros(2 * 2048, dtype=np.uint64)
+    emu.emu_blind_rotate(_p(emu_fbsk), _p(small), _p(lut), _p(acc), -1)
+    ref = tfhe.bootstrap_small(server_key, small, lut)
+    assert (tfhe.sample_extract(acc) == ref).all()
