@@ -95,16 +95,13 @@ FB_HD uint64_t from_torus(double t) {
 #endif
 }
 
-// ---- phase A: decompose (acc*X^a - acc) of polynomial accp into the folded, twisted FFT input ----
+// ---- phase A: decompose (acc*X^a - acc) of polynomial accp into the folded FFT input (digits; untwisted) ----
 FB_HD void phaseA_load(double (&xr)[32], double (&xi)[32], const uint64_t* accp, uint32_t a, int lane) {
 #pragma unroll
   for (int r = 0; r < 32; r++) {
     const uint32_t j = 32u * r + lane;
-    const double d0 = pbs_digit(rot_read(accp, j, a) - accp[j]);
-    const double d1 = pbs_digit(rot_read(accp, j + 1024u, a) - accp[j + 1024u]);
-    const double cr = fb_twist_cos(r), sr = fb_twist_sin(r);
-    xr[r] = fb_fma(d0, cr, -(d1 * sr));
-    xi[r] = fb_fma(d0, sr, d1 * cr);
+    xr[r] = pbs_digit(rot_read(accp, j, a) - accp[j]);
+    xi[r] = pbs_digit(rot_read(accp, j + 1024u, a) - accp[j + 1024u]);
   }
 }
 
@@ -131,11 +128,8 @@ FB_HD void phaseA_load32(double (&xr)[32], double (&xi)[32], const uint32_t* shp
 #pragma unroll
   for (int r = 0; r < 32; r++) {
     const uint32_t j = 32u * r + lane;
-    const double d0 = pbs_digit32(rot_read32(shp, j, a) - shp[j]);
-    const double d1 = pbs_digit32(rot_read32(shp, j + 1024u, a) - shp[j + 1024u]);
-    const double cr = fb_twist_cos(r), sr = fb_twist_sin(r);
-    xr[r] = fb_fma(d0, cr, -(d1 * sr));
-    xi[r] = fb_fma(d0, sr, d1 * cr);
+    xr[r] = pbs_digit32(rot_read32(shp, j, a) - shp[j]);               // the twist exp(i*pi*r/64) is folded
+    xi[r] = pbs_digit32(rot_read32(shp, j + 1024u, a) - shp[j + 1024u]);  // into fft32_fwd_twist
   }
 }
 
@@ -161,17 +155,14 @@ FB_HD void mac_point2(double& xr, double& xi, double pr, double pi, c2 b_own, c2
   xi = oi;
 }
 
-// same folding for a standard-domain key polynomial read as a signed torus value in [-1/2, 1/2)
+// same folding (untwisted) for a standard-domain key polynomial read as a signed torus value in [-1/2, 1/2)
 // (key conversion K7; tfhe-rs forward_as_torus)
 FB_HD void phaseA_load_torus(double (&xr)[32], double (&xi)[32], const uint64_t* poly, int lane) {
 #pragma unroll
   for (int r = 0; r < 32; r++) {
     const uint32_t j = 32u * r + lane;
-    const double d0 = (double)(int64_t)poly[j] * (1.0 / 18446744073709551616.0);
-    const double d1 = (double)(int64_t)poly[j + 1024u] * (1.0 / 18446744073709551616.0);
-    const double cr = fb_twist_cos(r), sr = fb_twist_sin(r);
-    xr[r] = fb_fma(d0, cr, -(d1 * sr));
-    xi[r] = fb_fma(d0, sr, d1 * cr);
+    xr[r] = (double)(int64_t)poly[j] * (1.0 / 18446744073709551616.0);
+    xi[r] = (double)(int64_t)poly[j + 1024u] * (1.0 / 18446744073709551616.0);
   }
 }
 

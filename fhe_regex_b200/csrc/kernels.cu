@@ -32,12 +32,12 @@ bsk_convert_kernel(const uint64_t* __restrict__ bsk_std, c2* __restrict__ fbsk, 
   const size_t row = blockIdx.x;  // (i * 2 + r)
   double xr[32], xi[32];
   phaseA_load_torus(xr, xi, bsk_std + (row * 2 + w) * kN, lane);
-  fft32_dif(xr, xi);
+  fft32_fwd_twist(xr, xi);
   fwd_twiddle_store(xr, xi, tbuf + w * kHalfN, tab_f, lane);
   __syncthreads();
   const int pp = lane >> 4, k1 = 16 * w + (lane & 15);
   phaseB_load(xr, xi, tbuf + pp * kHalfN, k1);
-  fft32_dif(xr, xi);
+  fft32_fwd(xr, xi);
   c2* dst = fbsk + (row * 2 + pp) * kHalfN + k1;
 #pragma unroll
   for (int q = 0; q < 32; q++) {
@@ -338,7 +338,7 @@ blind_rotate_kernel(const c2* __restrict__ fbsk, const uint64_t* __restrict__ sm
       }
       // phase A: this warp's polynomial -> digits -> folded/twisted -> pass 1 -> twiddle -> transpose (re, im)
       phaseA_load32(xr, xi, shp, a & 4095u, lane);
-      fft32_dif(xr, xi);
+      fft32_fwd_twist(xr, xi);
       fwd_twiddle_inplace(xr, xi, tab_f, lane);
       bar_sync(bar_id, 64);                       // previous readers of the plane are done
       col_store_brev(xr, plane + w * kHalfN, lane);
@@ -349,7 +349,7 @@ blind_rotate_kernel(const c2* __restrict__ fbsk, const uint64_t* __restrict__ sm
       bar_sync(bar_id, 64);
       row_load(xi, plane + pp * kHalfN, k1);
       // phase B: pass 2 -> Fourier MAC with the staged GGSW_i -> inverse pass 1 -> twiddle -> transpose
-      fft32_dif(xr, xi);
+      fft32_fwd(xr, xi);
       mbar_wait(full_bar, par);
 #pragma unroll
       for (int q = 0; q < 32; q++) {
@@ -359,7 +359,7 @@ blind_rotate_kernel(const c2* __restrict__ fbsk, const uint64_t* __restrict__ sm
         mac_point2(xr[q], xi[q], pr, pi, b_own[32 * k2], b_in[32 * k2]);
       }
       release_stage(i);                           // this warp no longer reads the stage
-      fft32_dit_inv(xr, xi);
+      fft32_inv(xr, xi);
       inv_twiddle_inplace(xr, xi, tab_i, k1);
       bar_sync(bar_id, 64);
       row_store(xr, plane + pp * kHalfN, k1);
@@ -370,7 +370,7 @@ blind_rotate_kernel(const c2* __restrict__ fbsk, const uint64_t* __restrict__ sm
       bar_sync(bar_id, 64);
       col_load_brev(xi, plane + w * kHalfN, lane);
       // phase C: inverse pass 2 -> untwist, round to torus, accumulate into TMEM, refresh the shadow
-      fft32_dit_inv(xr, xi);
+      fft32_inv(xr, xi);
 #pragma unroll
       for (int g = 0; g < 8; g++) {
         uint32_t v[16];

@@ -29,7 +29,7 @@ static void forward_passes(Sample& s) {
   for (int w = 0; w < 2; w++)
     for (int lane = 0; lane < 32; lane++) {
       Regs& R = s.regs[w][lane];
-      fft32_dif(R.xr, R.xi);
+      fft32_fwd_twist(R.xr, R.xi);   // input: untwisted folded coefficients
       fwd_twiddle_inplace(R.xr, R.xi, g_tab_f, lane);
     }
   // barrier; re plane
@@ -43,7 +43,7 @@ static void forward_passes(Sample& s) {
   for (int w = 0; w < 2; w++)
     for (int lane = 0; lane < 32; lane++) row_load(s.regs[w][lane].xi, s.plane.data() + (lane >> 4) * kHalfN, 16 * w + (lane & 15));
   for (int w = 0; w < 2; w++)
-    for (int lane = 0; lane < 32; lane++) fft32_dif(s.regs[w][lane].xr, s.regs[w][lane].xi);
+    for (int lane = 0; lane < 32; lane++) fft32_fwd(s.regs[w][lane].xr, s.regs[w][lane].xi);
 }
 
 // inverse half: inverse pass 1, twiddle, split transpose, inverse pass 2 (leaves phase-C input in regs)
@@ -51,7 +51,7 @@ static void inverse_passes(Sample& s) {
   for (int w = 0; w < 2; w++)
     for (int lane = 0; lane < 32; lane++) {
       Regs& R = s.regs[w][lane];
-      fft32_dit_inv(R.xr, R.xi);
+      fft32_inv(R.xr, R.xi);
       inv_twiddle_inplace(R.xr, R.xi, g_tab_i, 16 * w + (lane & 15));
     }
   for (int w = 0; w < 2; w++)
@@ -63,7 +63,7 @@ static void inverse_passes(Sample& s) {
   for (int w = 0; w < 2; w++)
     for (int lane = 0; lane < 32; lane++) col_load_brev(s.regs[w][lane].xi, s.plane.data() + w * kHalfN, lane);
   for (int w = 0; w < 2; w++)
-    for (int lane = 0; lane < 32; lane++) fft32_dit_inv(s.regs[w][lane].xr, s.regs[w][lane].xi);
+    for (int lane = 0; lane < 32; lane++) fft32_inv(s.regs[w][lane].xr, s.regs[w][lane].xi);
 }
 
 extern "C" void emu_bsk_to_fourier(const uint64_t* bsk, c2* fbsk) {
@@ -156,9 +156,7 @@ extern "C" void emu_negacyclic_mul(const int64_t* a_int, const uint64_t* b_torus
     // warp 0 <- polynomial under test, warp 1 <- zero
     for (int r = 0; r < 32; r++) {
       const int j = 32 * r + lane;
-      const double d0 = (double)a_int[j], d1 = (double)a_int[j + 1024];
-      const double cr = fb_twist_cos(r), sr = fb_twist_sin(r);
-      sa.regs[0][lane].xr[r] = d0 * cr - d1 * sr; sa.regs[0][lane].xi[r] = d0 * sr + d1 * cr;
+      sa.regs[0][lane].xr[r] = (double)a_int[j]; sa.regs[0][lane].xi[r] = (double)a_int[j + 1024];
       sa.regs[1][lane].xr[r] = 0; sa.regs[1][lane].xi[r] = 0;
     }
     phaseA_load_torus(sb.regs[0][lane].xr, sb.regs[0][lane].xi, b_torus, lane);
@@ -184,19 +182,3 @@ extern "C" void emu_negacyclic_mul(const int64_t* a_int, const uint64_t* b_torus
   memcpy(out, sa.acc.data(), sizeof(uint64_t) * kN);
 }
 
-// test hook: raw forward passes on already folded+twisted-by-register input z[32*r+lane] (poly 0 slot)
-extern "C" void emu_forward_raw(const double* zr, const double* zi, double* outr, double* outi) {
-  tabs();
-  Sample s;
-  for (int lane = 0; lane < 32; lane++)
-    for (int r = 0; r < 32; r++) {
-      s.regs[0][lane].xr[r] = zr[32 * r + lane]; s.regs[0][lane].xi[r] = zi[32 * r + lane];
-      s.regs[1][lane].xr[r] = 0; s.regs[1][lane].xi[r] = 0;
-    }
-  forward_passes(s);
-  for (int w = 0; w < 2; w++)
-    for (int lane = 0; lane < 16; lane++) {
-      const int k1 = 16 * w + lane;
-      for (int q = 0; q < 32; q++) { outr[k1 + 32 * brev5(q)] = s.regs[w][lane].xr[q]; outi[k1 + 32 * brev5(q)] = s.regs[w][lane].xi[q]; }
-    }
-}

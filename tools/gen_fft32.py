@@ -1,99 +1,192 @@
 #!/usr/bin/env python3
-"""Emit fhe_regex_b200/csrc/fft32_gen.h: straight-line, constant-indexed 32-point complex FFTs
-that live entirely in registers (one per thread), plus the per-register twist constants.
+"""Emit fhe_regex_b200/csrc/fft32_gen.h: straight-line 32-point complex FFTs that live entirely in the
+registers of one thread (constant indices only, so nvcc never spills the arrays to local memory).
 
-  fft32_dif(xr, xi)      forward, W = exp(-2*pi*i/32), natural order in -> bit-reversed order out
-  fft32_dit_inv(xr, xi)  inverse (conjugate twiddles, unnormalised), bit-reversed in -> natural out
+All three transforms are decimation-in-time butterflies whose twiddle multiplications are done with the
+"tangent" form: w*b = c*[(br - t*bi) + i(bi + t*br)], t = s/c (2 FMA instead of 2 MUL + 2 FMA), the real
+factor c being carried as a compile-time pending magnitude of b and folded into the constant of the
+following a +- rho*b (an FMA in place of an ADD).  In a DIT network every output inherits the pending
+magnitude of input position 0, which is 1, so nothing is left to normalise at the end.  A generic
+butterfly costs 6 FP64 issue slots instead of 8, and the input twist of the negacyclic transform
+(exp(i*pi*r/64) on register r) is folded in as one more pending rotation: 2 slots instead of 4.
 
-Straight-line code with literal twiddles keeps every index a compile-time constant so nvcc keeps
-xr/xi in registers (no local memory) and folds twiddles into DFMA immediates.
+  fft32_fwd_twist(xr, xi)  in : xr[r] = d0, xi[r] = d1 (integer digits of coefficients 32r+lane, +1024)
+                           out: register q holds X[brev5(q)] of the forward DFT (W = exp(-2*pi*i/32)) of
+                                (d0 + i*d1) * exp(i*pi*r/64)
+  fft32_fwd(xr, xi)        natural in, register q holds X[brev5(q)] out, forward DFT
+  fft32_inv(xr, xi)        register q holds Y[brev5(q)] in, natural out, inverse DFT (unnormalised)
+
+The generator checks every emitted routine numerically (numpy float64 replay against a direct DFT).
 """
 import math
 import os
-
-import numpy as np
 from fractions import Fraction
 
-LD = np.longdouble  # x87 80-bit: twiddle literals are correctly rounded doubles
+import numpy as np
+
+LD = np.longdouble
 LD_PI = LD("3.141592653589793238462643383279502884")
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "fhe_regex_b200", "csrc", "fft32_gen.h")
 
 
-def cs(num, den):
-    """cos/sin of 2*pi*num/den, exact for the axis/diagonal cases."""
-    f = Fraction(num, den) % 1
-    table = {Fraction(0): (1.0, 0.0), Fraction(1, 4): (0.0, 1.0), Fraction(1, 2): (-1.0, 0.0), Fraction(3, 4): (0.0, -1.0)}
-    if f in table:
-        return table[f]
-    a = 2 * LD_PI * LD(f.numerator) / LD(f.denominator)
-    return float(np.cos(a)), float(np.sin(a))
+def brev5(v):
+    return int("{:05b}".format(v)[::-1], 2)
+
+
+def cs_frac(fr):
+    """(cos, sin) of 2*pi*fr in long double, exact on the axes and diagonals."""
+    fr = fr % 1
+    table = {Fraction(0): (1, 0), Fraction(1, 4): (0, 1), Fraction(1, 2): (-1, 0), Fraction(3, 4): (0, -1)}
+    if fr in table:
+        c, s = table[fr]
+        return LD(c), LD(s)
+    if (fr * 8).denominator == 1:
+        r = LD(0.5) ** LD(0.5)
+        e = int(fr * 8)
+        return {1: (r, r), 3: (-r, r), 5: (-r, -r), 7: (r, -r)}[e]
+    a = 2 * LD_PI * LD(fr.numerator) / LD(fr.denominator)
+    return np.cos(a), np.sin(a)
 
 
 def lit(x):
     return repr(float(x))
 
 
-R2 = lit(math.sqrt(0.5))
+class Emitter:
+    """Tracks, per array slot, stored value -> true value = sign * mag * stored (sign per component)."""
+
+    def __init__(self):
+        self.lines = []
+        self.mag = [LD(1)] * 32
+        self.sr = [1] * 32
+        self.si = [1] * 32
+        self.slots = 0  # FP64 issue slots emitted
+
+    def emit(self, s):
+        self.lines.append(s)
+
+    def rotate(self, p, c, s):
+        """slot p *= (c + i s), |c+is| = 1, by the tangent form; updates pending magnitude / signs."""
+        if abs(s) < 1e-30:  # +-1
+            if c < 0:
+                self.sr[p] = -self.sr[p]
+                self.si[p] = -self.si[p]
+            return
+        if abs(c) < 1e-30:  # +-i : (re, im) -> (-+im, +-re)
+            self.emit(f"{{ const double t_ = xr[{p}]; xr[{p}] = xi[{p}]; xi[{p}] = t_; }}")
+            nsr = -self.si[p] * (1 if s > 0 else -1)
+            nsi = self.sr[p] * (1 if s > 0 else -1)
+            self.sr[p], self.si[p] = nsr, nsi
+            return
+        if abs(c) >= abs(s):
+            # true_re = c*Sr*m*[Br - (s*Si/(c*Sr))*Bi] ; true_im = c*Si*m*[Bi + (s*Sr/(c*Si))*Br]
+            kr = -(s * self.si[p]) / (c * self.sr[p])
+            ki = (s * self.sr[p]) / (c * self.si[p])
+            self.emit(f"{{ const double t_ = xr[{p}]; xr[{p}] = {self.fma('xi[%d]' % p, kr, 't_')}; xi[{p}] = {self.fma('t_', ki, 'xi[%d]' % p)}; }}")
+            f = c
+        else:
+            # true_re = -s*Si*m*[Bi - (c*Sr/(s*Si))*Br] -> stored re' = Bi + k*Br with sign -sgn(s)*Si
+            # true_im =  s*Sr*m*[Br + (c*Si/(s*Sr))*Bi]
+            kr = -(c * self.sr[p]) / (s * self.si[p])
+            ki = (c * self.si[p]) / (s * self.sr[p])
+            self.emit(f"{{ const double t_ = xr[{p}]; xr[{p}] = {self.fma('t_', kr, 'xi[%d]' % p)}; xi[{p}] = {self.fma('xi[%d]' % p, ki, 't_')}; }}")
+            nsr = -self.si[p] * (1 if s > 0 else -1)
+            nsi = self.sr[p] * (1 if s > 0 else -1)
+            self.sr[p], self.si[p] = nsr, nsi
+            self.mag[p] = self.mag[p] * abs(s)
+            self.slots += 2
+            return
+        if f < 0:
+            self.sr[p] = -self.sr[p]
+            self.si[p] = -self.si[p]
+        self.mag[p] = self.mag[p] * abs(f)
+        self.slots += 2
+
+    def fma(self, x, k, y):
+        """C expression for x*k + y with the +-1 cases as plain add/sub."""
+        kf = float(k)
+        if kf == 1.0:
+            return f"{y} + {x}"
+        if kf == -1.0:
+            return f"{y} - {x}"
+        return f"fb_fma({x}, {lit(kf)}, {y})"
+
+    def butterfly(self, a, b):
+        """(a, b) <- (a + b, a - b) in true values; results inherit a's pending magnitude and signs."""
+        rr = (self.sr[b] * self.mag[b]) / (self.sr[a] * self.mag[a])
+        ri = (self.si[b] * self.mag[b]) / (self.si[a] * self.mag[a])
+        self.emit(f"{{ const double tr_ = xr[{b}], ti_ = xi[{b}]; "
+                  f"xr[{b}] = {self.fma('tr_', -rr, 'xr[%d]' % a)}; xi[{b}] = {self.fma('ti_', -ri, 'xi[%d]' % a)}; "
+                  f"xr[{a}] = {self.fma('tr_', rr, 'xr[%d]' % a)}; xi[{a}] = {self.fma('ti_', ri, 'xi[%d]' % a)}; }}")
+        self.mag[b], self.sr[b], self.si[b] = self.mag[a], self.sr[a], self.si[a]
+        self.slots += 4
+
+    def finish(self):
+        for p in range(32):
+            assert abs(float(self.mag[p]) - 1.0) < 1e-15 and self.sr[p] == 1 and self.si[p] == 1, (p, self.mag[p], self.sr[p], self.si[p])
 
 
-def emit_mul(lines, tr, ti, outr, outi, num, den, sign):
-    """(outr + i outi) = (tr + i ti) * exp(sign*2*pi*i*num/den), with special cases."""
-    f = (Fraction(num, den) * sign) % 1
-    eighth = f * 8
-    if eighth.denominator == 1:
-        e = int(eighth) % 8
-        if e == 0:
-            lines.append(f"{outr} = {tr}; {outi} = {ti};")
-        elif e == 2:  # * i
-            lines.append(f"{outr} = -{ti}; {outi} = {tr};")
-        elif e == 4:
-            lines.append(f"{outr} = -{tr}; {outi} = -{ti};")
-        elif e == 6:  # * -i
-            lines.append(f"{outr} = {ti}; {outi} = -{tr};")
-        elif e == 1:  # (1+i)/sqrt2
-            lines.append(f"{outr} = ({tr} - {ti}) * {R2}; {outi} = ({tr} + {ti}) * {R2};")
-        elif e == 3:  # (-1+i)/sqrt2
-            lines.append(f"{outr} = (-{tr} - {ti}) * {R2}; {outi} = ({tr} - {ti}) * {R2};")
-        elif e == 5:  # (-1-i)/sqrt2
-            lines.append(f"{outr} = ({ti} - {tr}) * {R2}; {outi} = (-{tr} - {ti}) * {R2};")
-        elif e == 7:  # (1-i)/sqrt2
-            lines.append(f"{outr} = ({tr} + {ti}) * {R2}; {outi} = ({ti} - {tr}) * {R2};")
-        return
-    c, s = cs(f.numerator, f.denominator)
-    lines.append(f"{outr} = fb_fma({tr}, {lit(c)}, -({ti} * {lit(s)})); {outi} = fb_fma({tr}, {lit(s)}, {ti} * {lit(c)});")
-
-
-def gen_dif():
-    L = []
-    half = 16
-    while half >= 1:
-        for g in range(0, 32, 2 * half):
-            for j in range(half):
-                a, b = g + j, g + j + half
-                L.append(f"tr = xr[{a}] - xr[{b}]; ti = xi[{a}] - xi[{b}]; xr[{a}] += xr[{b}]; xi[{a}] += xi[{b}];")
-                emit_mul(L, "tr", "ti", f"xr[{b}]", f"xi[{b}]", j, 2 * half, -1)
-        half //= 2
-    return L
-
-
-def gen_dit_inv():
-    L = []
+def gen_dit(sign, slot_of_pos, twist):
+    """DIT network over positions 0..31 (position p holds input x[brev5(p)]); array slot = slot_of_pos(p).
+    sign = -1 forward, +1 inverse.  twist: pre-rotation exp(i*pi*r/64) of natural input index r."""
+    E = Emitter()
+    if twist:
+        for p in range(32):
+            r = brev5(p)  # natural input index held at position p
+            c, s = cs_frac(Fraction(r, 128))
+            E.rotate(slot_of_pos(p), c, s)
     half = 1
     while half <= 16:
         for g in range(0, 32, 2 * half):
             for j in range(half):
                 a, b = g + j, g + j + half
-                emit_mul(L, f"xr[{b}]", f"xi[{b}]", "tr", "ti", j, 2 * half, +1)
-                L.append(f"xr[{b}] = xr[{a}] - tr; xi[{b}] = xi[{a}] - ti; xr[{a}] += tr; xi[{a}] += ti;")
+                c, s = cs_frac(Fraction(sign * j, 2 * half))
+                E.rotate(slot_of_pos(b), c, s)
+                E.butterfly(slot_of_pos(a), slot_of_pos(b))
         half *= 2
-    return L
+    E.finish()
+    return E
+
+
+def replay(lines, xr, xi):
+    """execute the emitted C statements with numpy float64 semantics (fma -> separate mul/add: fine for a check)"""
+    env = {"xr": xr, "xi": xi, "fb_fma": lambda a, b, c: a * b + c}
+    for ln in lines:
+        body = ln.strip()
+        assert body.startswith("{") and body.endswith("}")
+        for st in body[1:-1].split(";"):
+            st = st.strip()
+            if not st:
+                continue
+            if st.startswith("const double"):
+                for decl in st[len("const double"):].split(","):
+                    name, expr = decl.split("=")
+                    env[name.strip()] = eval(expr, {}, env)
+            else:
+                lhs, expr = st.split("=", 1)
+                val = eval(expr, {}, env)
+                arr, idx = lhs.strip().split("[")
+                env[arr][int(idx[:-1])] = val
+
+
+def check(E, sign, slot_of_pos, twist, out_slot_of_k):
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal(32) + 1j * rng.standard_normal(32)
+    xr, xi = np.zeros(32), np.zeros(32)
+    for p in range(32):
+        n = brev5(p)
+        xr[slot_of_pos(p)], xi[slot_of_pos(p)] = x[n].real, x[n].imag
+    replay(E.lines, xr, xi)
+    xin = x * np.exp(1j * np.pi * np.arange(32) / 64) if twist else x
+    ref = np.array([sum(xin[n] * np.exp(sign * 2j * np.pi * n * k / 32) for n in range(32)) for k in range(32)])
+    got = np.array([xr[out_slot_of_k(k)] + 1j * xi[out_slot_of_k(k)] for k in range(32)])
+    err = np.abs(got - ref).max()
+    assert err < 1e-12, err
+    return err
 
 
 def main():
-    out = []
-    out.append("// GENERATED by tools/gen_fft32.py -- do not edit.")
-    out.append("#pragma once")
-    out.append("")
+    out = ["// GENERATED by tools/gen_fft32.py -- do not edit.", "#pragma once", ""]
     out.append("// twist exp(i*pi*r/64) for register r (coefficient index 32*r + lane); switch on a constant folds to an immediate")
     for name, fn in (("cos", np.cos), ("sin", np.sin)):
         out.append(f"FB_HD constexpr double fb_twist_{name}(int r) {{")
@@ -104,15 +197,21 @@ def main():
         out.append("  return 0.0;")
         out.append("}")
     out.append("")
-    out.append("FB_HD void fft32_dif(double (&xr)[32], double (&xi)[32]) {")
-    out.append("  double tr, ti;")
-    out += ["  " + l for l in gen_dif()]
-    out.append("}")
-    out.append("")
-    out.append("FB_HD void fft32_dit_inv(double (&xr)[32], double (&xi)[32]) {")
-    out.append("  double tr, ti;")
-    out += ["  " + l for l in gen_dit_inv()]
-    out.append("}")
+    # forward: natural input index r sits in array slot r; position p holds x[brev5(p)] -> slot brev5(p);
+    # output X[k] ends at position k = slot brev5(k): "register q holds X[brev5(q)]"
+    fwd_slot = brev5
+    # inverse: slot q holds Y[brev5(q)] = the input of position q; output natural: y[n] at slot n
+    inv_slot = lambda p: p
+    specs = [("fft32_fwd_twist", -1, fwd_slot, True, brev5), ("fft32_fwd", -1, fwd_slot, False, brev5), ("fft32_inv", +1, inv_slot, False, lambda k: k)]
+    for name, sign, slot, twist, outslot in specs:
+        E = gen_dit(sign, slot, twist)
+        err = check(E, sign, slot, twist, outslot)
+        print(f"{name}: {E.slots} FP64 slots, replay max err {err:.2e}")
+        out.append(f"// {E.slots} FP64 issue slots")
+        out.append(f"FB_HD void {name}(double (&xr)[32], double (&xi)[32]) {{")
+        out += ["  " + l for l in E.lines]
+        out.append("}")
+        out.append("")
     with open(OUT, "w") as f:
         f.write("\n".join(out) + "\n")
     print("wrote", os.path.normpath(OUT), len(out), "lines")
