@@ -73,10 +73,10 @@ extern "C" void fb_ctx_destroy(fb_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (auto& p : ctx->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (auto& p : ctx->pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
-  cudaFree(ctx->d_ksk);
+  cudaFree(ctx->d_kb);
   cudaFree(ctx->d_fbsk);
   cudaFree(ctx->d_tabs);
-  for (fb_devbuf* b : {&ctx->in, &ctx->small, &ctx->out, &ctx->luts, &ctx->lut_idx}) cudaFree(b->p);
+  for (fb_devbuf* b : {&ctx->in, &ctx->small, &ctx->out, &ctx->luts, &ctx->lut_idx, &ctx->digits}) cudaFree(b->p);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -92,9 +92,17 @@ extern "C" int fb_sync(fb_ctx* ctx) {
 extern "C" int fb_load_server_key_raw(fb_ctx* ctx, const uint64_t* h_ksk, const uint64_t* h_bsk_std) {
   if (!ctx || !h_ksk || !h_bsk_std) return fb_fail(ctx, FB_ERR_ARG, "null argument");
   FB_CUDA(ctx, cudaSetDevice(ctx->device));
-  if (!ctx->d_ksk) FB_CUDA(ctx, cudaMalloc(&ctx->d_ksk, FB_KSK_WORDS * sizeof(uint64_t)));
   if (!ctx->d_fbsk) FB_CUDA(ctx, cudaMalloc(&ctx->d_fbsk, (size_t)fb::kLweN * 4 * fb::kHalfN * sizeof(c2)));
-  FB_CUDA(ctx, cudaMemcpyAsync(ctx->d_ksk, h_ksk, FB_KSK_WORDS * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+  if (!ctx->d_kb) FB_CUDA(ctx, cudaMalloc(&ctx->d_kb, fb::ks_key_bytes()));
+  uint64_t* d_ksk = nullptr;  // staging copy of the u64 key; only its byte planes stay resident
+  FB_CUDA(ctx, cudaMalloc(&d_ksk, FB_KSK_WORDS * sizeof(uint64_t)));
+  {
+    cudaError_t e = cudaMemcpyAsync(d_ksk, h_ksk, FB_KSK_WORDS * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = fb::launch_ksk_bytes(d_ksk, ctx->d_kb, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_ksk);
+    if (e != cudaSuccess) return fb_cuda_fail(ctx, e, "keyswitch key upload / byte-plane split");
+  }
   uint64_t* d_std = nullptr;
   FB_CUDA(ctx, cudaMalloc(&d_std, FB_BSK_WORDS * sizeof(uint64_t)));
   cudaError_t e = cudaMemcpyAsync(d_std, h_bsk_std, FB_BSK_WORDS * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
@@ -173,9 +181,11 @@ static void timing_end(fb_ctx* ctx, bool on, fb_event_pair& ev) {
 }
 
 int fb_run_keyswitch(fb_ctx* ctx, const uint64_t* d_in, const int32_t* d_in_rows, uint64_t* d_small, int count) {
+  int rc = fb_reserve(ctx, ctx->digits, fb::ks_digit_bytes(count));
+  if (rc) return rc;
   fb_event_pair ev;
   bool t = timing_begin(ctx, 0, ev);
-  cudaError_t e = fb::launch_keyswitch(ctx->d_ksk, d_in, d_in_rows, d_small, count, ctx->stream);
+  cudaError_t e = fb::launch_keyswitch_mma(ctx->d_kb, (int8_t*)ctx->digits.p, d_in, d_in_rows, d_small, count, ctx->stream);
   timing_end(ctx, t, ev);
   if (e != cudaSuccess) return fb_cuda_fail(ctx, e, "keyswitch_kernel launch");
   ctx->ks.ks_launches++;

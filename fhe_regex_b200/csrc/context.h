@@ -22,12 +22,12 @@ struct fb_ctx {
   cudaStream_t stream = nullptr;
   std::string err;
   // keys
-  uint64_t* d_ksk = nullptr;
+  uint8_t* d_kb = nullptr;     // byte planes of the KSK for the tensor-core keyswitch
   fb::c2* d_fbsk = nullptr;
   fb::c2* d_tabs = nullptr;
   bool have_key = false;
   // scratch for the batch entry points
-  fb_devbuf in, small, out, luts, lut_idx;
+  fb_devbuf in, small, out, luts, lut_idx, digits;
   // timing
   bool timing = false;
   std::vector<fb_event_pair> pending;

@@ -2,7 +2,7 @@
 //
 // Replaces the tfhe-rs 0.2.0 arithmetic under fhe-regex's six smart_* call sites
 // (/root/reference/src/regex/execution.rs:76,93,110,143,173,190) -- SURVEY.md section 2, kernels K1-K5, K7.
-//   K1 keyswitch_kernel          exact mod-2^64 LWE x KSK gadget contraction
+//   K1 (ks_kernels.cu)           exact mod-2^64 LWE x KSK gadget contraction on the int8 tensor cores
 //   K2-K4 blind_rotate_kernel    modulus switch + LUT accumulator init, 742 CMUX steps with an f64
 //                                 negacyclic FFT external product, sample extract -- one launch
 //   K5 lincomb_kernel            sum_i c_i * ct_i + trivial(const)
@@ -45,87 +45,6 @@ bsk_convert_kernel(const uint64_t* __restrict__ bsk_std, c2* __restrict__ fbsk, 
     v.x = xr[q];
     v.y = xi[q];
     dst[32 * brev5(q)] = v;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// K1: keyswitch.  out[b][c] = [c==742]*in[b][2048] - sum_{i<2048} sum_{l<5} d(b,i,l) * KSK[i][l][c]
-// CTA tile: KS_TB samples x 256 output columns; the KSK slice is read once per tile and reused
-// across the KS_TB samples held in registers; digits are decomposed once per chunk into smem.
-// ------------------------------------------------------------------------------------------------
-constexpr int KS_TB = 8;
-constexpr int KS_CH = 256;
-
-__device__ __forceinline__ uint32_t ks_pack_digits(uint64_t x) {
-  // closest representable on the top 15 bits, then 5 balanced base-8 digits, least significant first;
-  // the digit produced at iteration t multiplies KSK level row l = 4 - t (rows are stored most
-  // significant level first).  Packed as 5 signed nibbles, nibble l = digit for row l.
-  uint32_t state = (uint32_t)((((x >> 48) + 1ull) >> 1) & 0x7FFFull);
-  uint32_t packed = 0;
-#pragma unroll
-  for (int t = 0; t < kKsLevels; t++) {
-    uint32_t res = state & 7u;
-    state >>= 3;
-    uint32_t carry = (((res - 1u) | state) & res) >> 2;
-    state += carry;
-    uint32_t digit = (res - (carry << 3)) & 0xFu;
-    packed |= digit << (4 * (kKsLevels - 1 - t));
-  }
-  return packed;
-}
-
-__global__ void __launch_bounds__(256)
-keyswitch_kernel(const uint64_t* __restrict__ ksk, const uint64_t* __restrict__ in, const int32_t* __restrict__ in_rows,
-                 uint64_t* __restrict__ out, int count) {
-  __shared__ uint32_t dig[KS_TB][KS_CH];
-  __shared__ const uint64_t* src[KS_TB];
-  const int tid = threadIdx.x;
-  const int b0 = blockIdx.x * KS_TB;
-  const int col = blockIdx.y * 256 + tid;
-  const bool col_ok = col < kSmall;
-  const int colc = col_ok ? col : kSmall - 1;
-  if (tid < KS_TB) {
-    int b = b0 + tid;
-    if (b >= count) b = count - 1;
-    const size_t row = in_rows ? (size_t)in_rows[b] : (size_t)b;
-    src[tid] = in + row * kBig;
-  }
-  __syncthreads();
-  uint64_t acc[KS_TB];
-#pragma unroll
-  for (int b = 0; b < KS_TB; b++) acc[b] = 0;
-
-  for (int chunk = 0; chunk < kN / KS_CH; chunk++) {
-#pragma unroll
-    for (int b = 0; b < KS_TB; b++) dig[b][tid] = ks_pack_digits(src[b][chunk * KS_CH + tid]);
-    __syncthreads();
-    const uint64_t* kp = ksk + ((size_t)chunk * KS_CH * kKsLevels) * kSmall + colc;
-#pragma unroll 2
-    for (int ii = 0; ii < KS_CH; ii++) {
-      uint64_t k[kKsLevels];
-#pragma unroll
-      for (int l = 0; l < kKsLevels; l++) k[l] = __ldg(kp + ((size_t)ii * kKsLevels + l) * kSmall);
-#pragma unroll
-      for (int b = 0; b < KS_TB; b++) {
-        const int32_t p = (int32_t)dig[b][ii];
-#pragma unroll
-        for (int l = 0; l < kKsLevels; l++) {
-          const int32_t d = (p << (28 - 4 * l)) >> 28;  // sign-extended nibble l
-          acc[b] -= (uint64_t)(int64_t)d * k[l];
-        }
-      }
-    }
-    __syncthreads();
-  }
-  if (col_ok) {
-#pragma unroll
-    for (int b = 0; b < KS_TB; b++) {
-      if (b0 + b < count) {
-        uint64_t v = acc[b];
-        if (col == kLweN) v += src[b][kN];
-        out[(size_t)(b0 + b) * kSmall + col] = v;
-      }
-    }
   }
 }
 
@@ -480,14 +399,6 @@ cudaError_t launch_bsk_convert(const uint64_t* bsk_std, c2* fbsk, const c2* tabs
   cudaError_t e = cudaFuncSetAttribute(bsk_convert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   bsk_convert_kernel<<<kLweN * 2, 64, smem, st>>>(bsk_std, fbsk, tabs);
-  return cudaGetLastError();
-}
-
-cudaError_t launch_keyswitch(const uint64_t* ksk, const uint64_t* in, const int32_t* in_rows, uint64_t* out, int count,
-                             cudaStream_t st) {
-  if (count <= 0) return cudaSuccess;
-  dim3 grid((count + KS_TB - 1) / KS_TB, (kSmall + 255) / 256);
-  keyswitch_kernel<<<grid, 256, 0, st>>>(ksk, in, in_rows, out, count);
   return cudaGetLastError();
 }
 

@@ -7,12 +7,16 @@
 namespace fb {
 size_t br_smem_bytes(int S);
 cudaError_t launch_bsk_convert(const uint64_t* bsk_std, c2* fbsk, const c2* tabs, cudaStream_t st);
-cudaError_t launch_keyswitch(const uint64_t* ksk, const uint64_t* in, const int32_t* in_rows, uint64_t* out, int count,
-                             cudaStream_t st);
 cudaError_t launch_blind_rotate(const c2* fbsk, const uint64_t* small, const uint64_t* luts, const uint32_t* lut_idx,
                                 uint64_t* out, const int32_t* out_rows, const c2* tabs, int count, cudaStream_t st);
 cudaError_t launch_lincomb(uint64_t* arena, const int32_t* out_rows, const int32_t* term_off, const int32_t* term_rows,
                            const int64_t* term_coef, const uint64_t* body_const, int n_out, cudaStream_t st);
+// keyswitch as an int8 tensor-core contraction (ks_kernels.cu)
+size_t ks_key_bytes();
+size_t ks_digit_bytes(int count);
+cudaError_t launch_ksk_bytes(const uint64_t* ksk, uint8_t* kb, cudaStream_t st);
+cudaError_t launch_keyswitch_mma(const uint8_t* kb, int8_t* dig, const uint64_t* in, const int32_t* in_rows, uint64_t* out, int count,
+                                 cudaStream_t st);
 cudaError_t launch_fp64_peak(double* sink, int ctas, cudaStream_t st);
 double fp64_peak_flops_per_launch(int ctas);
 int br_samples_per_cta();
