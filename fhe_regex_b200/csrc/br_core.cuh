@@ -21,6 +21,7 @@
 #pragma once
 #include <stdint.h>
 #include <math.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define FB_HD static __host__ __device__ __forceinline__
@@ -105,39 +106,70 @@ FB_HD void phaseA_load(double (&xr)[32], double (&xi)[32], const uint64_t* accp,
   }
 }
 
-// ---- 32-bit shadow accumulator ---------------------------------------------------------------
-// The 64-bit accumulator of a sample lives thread-privately (tensor memory on the device); shared
-// memory only holds a 32-bit shadow -- the top word of every coefficient, rounded -- which is all the
-// decomposition of acc*X^a - acc needs: the digit keeps 23 bits, so a 32-bit difference moves the
-// closest-representable rounding point by at most 2^-32 (the f64 FFT error is ~2^-15).
-FB_HD uint32_t shadow_word(uint64_t a) { return (uint32_t)((a + 0x80000000ull) >> 32); }
-
-FB_HD uint32_t rot_read32(const uint32_t* shp, uint32_t j, uint32_t a) {
+// ---- 32-bit accumulator -------------------------------------------------------------------------
+// The accumulator of the blind rotation is kept on the top 32 torus bits.  Its increments come out of an
+// f64 inverse transform whose values have magnitude ~2^25 (digits up to 2^22 times 4096 key terms), i.e. a
+// granularity of ~2^-27 on the torus: the low word of a 64-bit accumulator would only ever collect zeros
+// and rounding dust.  Rounding every increment to 2^-32 adds at most 742 * 2^-66 / 12 of variance
+// (sigma < 2^-29) to an output whose FFT noise alone is ~2^-15.  With a 32-bit
+// accumulator the base-2^23 decomposition of acc*X^a - acc below is exact.
+FB_HD uint32_t rot_read32(const uint32_t* accp, uint32_t j, uint32_t a) {
   const uint32_t idx = (j - a) & 4095u;
-  const uint32_t v = shp[idx & 2047u];
+  const uint32_t v = accp[idx & 2047u];
   return (idx & 2048u) ? 0u - v : v;
 }
 
-// balanced base-2^23 digit of a 32-bit torus difference: round(diff / 2^9) in [-2^22, 2^22]
-FB_HD double pbs_digit32(uint32_t diff) {
-  const int32_t d = (int32_t)(diff + 256u) >> 9;
-  return (double)d;
+FB_HD double hilo_to_double(uint32_t hi, uint32_t lo) {
+#if defined(__CUDA_ARCH__)
+  return __hiloint2double((int)hi, (int)lo);
+#else
+  const uint64_t bits = ((uint64_t)hi << 32) | lo;
+  double d;
+  memcpy(&d, &bits, sizeof d);
+  return d;
+#endif
+}
+FB_HD uint32_t double_lo32(double d) {
+#if defined(__CUDA_ARCH__)
+  return (uint32_t)__double2loint(d);
+#else
+  uint64_t bits;
+  memcpy(&bits, &d, sizeof d);
+  return (uint32_t)bits;
+#endif
 }
 
-FB_HD void phaseA_load32(double (&xr)[32], double (&xi)[32], const uint32_t* shp, uint32_t a, int lane) {
+// balanced base-2^23 digit of a 32-bit torus difference, round(diff / 2^9) in [-2^22, 2^22], as a double.
+// int -> double without the conversion unit: the double 2^52 + 2^31 + q carries q + 2^31 in its low word.
+FB_HD double pbs_digit32(uint32_t diff) {
+  const int32_t q = (int32_t)(diff + 256u) >> 9;
+  return hilo_to_double(0x43300000u, (uint32_t)q ^ 0x80000000u) - 4503601774854144.0;  // 2^52 + 2^31
+}
+
+// decompose (acc*X^a - acc) of polynomial accp into the folded FFT input (digits; the twist is in fft32_fwd_twist)
+FB_HD void phaseA_load32(double (&xr)[32], double (&xi)[32], const uint32_t* accp, uint32_t a, int lane) {
 #pragma unroll
   for (int r = 0; r < 32; r++) {
     const uint32_t j = 32u * r + lane;
-    xr[r] = pbs_digit32(rot_read32(shp, j, a) - shp[j]);               // the twist exp(i*pi*r/64) is folded
-    xi[r] = pbs_digit32(rot_read32(shp, j + 1024u, a) - shp[j + 1024u]);  // into fft32_fwd_twist
+    xr[r] = pbs_digit32(rot_read32(accp, j, a) - accp[j]);
+    xi[r] = pbs_digit32(rot_read32(accp, j + 1024u, a) - accp[j + 1024u]);
   }
 }
 
+// fractional part of t as a 32-bit torus word, round(frac(t) * 2^32) mod 2^32, |t| < 2^51; magic-number
+// rounding on the FP64 pipe only (no F2I/FRND through the conversion unit)
+FB_HD uint32_t torus32_from_double(double t) {
+  const double kMagic = 6755399441055744.0;  // 1.5 * 2^52
+  const double ti = (t + kMagic) - kMagic;   // rint(t)
+  const double f = t - ti;                   // exact, in [-1/2, 1/2]
+  return double_lo32(fb_fma(f, 4294967296.0, kMagic));
+}
+
 // phase C for one register: torus increments of coefficients 32r+lane (re) and 32r+lane+1024 (im)
-FB_HD void phaseC_increments(const double (&xr)[32], const double (&xi)[32], int r, uint64_t& inc0, uint64_t& inc1) {
+FB_HD void phaseC_increments32(const double (&xr)[32], const double (&xi)[32], int r, uint32_t& inc0, uint32_t& inc1) {
   const double cr = fb_twist_cos(r) * (1.0 / 1024.0), sr = fb_twist_sin(r) * (1.0 / 1024.0);
-  inc0 = from_torus(fb_fma(xr[r], cr, xi[r] * sr));
-  inc1 = from_torus(fb_fma(xi[r], cr, -(xr[r] * sr)));
+  inc0 = torus32_from_double(fb_fma(xr[r], cr, xi[r] * sr));
+  inc1 = torus32_from_double(fb_fma(xi[r], cr, -(xr[r] * sr)));
 }
 
 // Fourier MAC of one frequency point: out = x * b_own + partner * b_in, where `partner` is the other

@@ -56,10 +56,11 @@ bsk_convert_kernel(const uint64_t* __restrict__ bsk_std, c2* __restrict__ fbsk, 
 // last to finish its Fourier MAC of step i (shared-memory arrival counter) issues the copy of step
 // i+1, which lands while the samples run their inverse transforms and the next forward transforms;
 // an mbarrier with a transaction count tells the consumers when the bytes are there.
-// The 64-bit accumulators live thread-privately in tensor memory (TMEM, tcgen05.ld/st); shared memory
-// holds only a 32-bit shadow for the rotation reads of the decomposition.
+// The accumulator is kept on 32 torus bits (br_core.cuh): every thread owns its 64 coefficients in tensor
+// memory (TMEM, tcgen05.ld/st) and mirrors them into shared memory for the rotation reads of the
+// decomposition.  No FP64<->integer conversion goes through the conversion unit (magic-number rounding).
 //
-// Shared memory: 64 KiB GGSW stage + S * (16 KiB u32 shadow accumulator + 16 KiB transpose plane)
+// Shared memory: 64 KiB GGSW stage + S * (16 KiB u32 accumulator + 16 KiB transpose plane)
 //                + 12 KiB twiddles + S * 1.5 KiB mod-switched mask + 768 B step flags + mbarrier.
 // ------------------------------------------------------------------------------------------------
 constexpr int kGgswBytes = 4 * kHalfN * (int)sizeof(c2);  // 65536
@@ -91,10 +92,10 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                : "memory");
 }
 
-// ---- tensor memory (TMEM) as thread-private storage of the 64-bit accumulators ----------------------
+// ---- tensor memory (TMEM) as thread-private storage of the accumulators ----------------------------
 // TMEM is 128 lanes x 512 32-bit columns per SM; warp w of a CTA may touch lanes 32*(w%4) .. +31 only, and
 // tcgen05.ld/st.32x32b hands thread `lane` consecutive columns of its own lane: exactly a 256 KiB
-// register-file extension.  Each consumer warp owns 128 columns (64 u64 coefficients per thread).
+// register-file extension.  Each warp owns 64 columns (its 64 u32 coefficients per thread).
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(64 * S, 1)
 blind_rotate_kernel(const c2* __restrict__ fbsk, const uint64_t* __restrict__ small, const uint64_t* __restrict__ luts,
                     const uint32_t* __restrict__ lut_idx, uint64_t* __restrict__ out, const int32_t* __restrict__ out_rows,
                     const c2* __restrict__ tabs_g, int count) {
-  static_assert(2 * S <= 16, "128 TMEM columns per consumer warp, 4 warps per lane quarter");
+  static_assert(2 * S <= 32, "64 TMEM columns per warp, 8 warps per lane quarter");
   extern __shared__ __align__(128) unsigned char smem[];
   c2* stage = reinterpret_cast<c2*>(smem);                                             // [2][2][1024]
   uint32_t* shadow_all = reinterpret_cast<uint32_t*>(smem + kGgswBytes);                // [S][2][2048]
@@ -211,28 +212,26 @@ blind_rotate_kernel(const c2* __restrict__ fbsk, const uint64_t* __restrict__ sm
   }
 
   if (active) {
-    uint32_t* shp = shadow_all + (size_t)s * 2 * kN + (size_t)w * kN;  // shadow of polynomial w of this sample
+    uint32_t* shp = shadow_all + (size_t)s * 2 * kN + (size_t)w * kN;  // shared copy of polynomial w of this sample
     double* plane = plane_all + (size_t)s * 2 * kHalfN;
     const int bar_id = 1 + s;
-    // this warp's 128 TMEM columns: coefficient 32r+lane in columns 4r,4r+1 (lo,hi), 32r+lane+1024 in 4r+2,4r+3
-    const uint32_t tacc = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 128);
+    // this warp's 64 TMEM columns: coefficient 32r+lane in column 2r, 32r+lane+1024 in column 2r+1
+    const uint32_t tacc = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 64);
 
-    // accumulator init: (0, lut * X^{-b})
+    // accumulator init: (0, lut * X^{-b}), top words
     {
       const uint64_t* lut = luts + (size_t)lut_idx[sample] * kN;
       const uint32_t rot = (4096u - (uint32_t)at[kLweN]) & 4095u;
 #pragma unroll 1
-      for (int g = 0; g < 8; g++) {
+      for (int g = 0; g < 4; g++) {
         uint32_t v[16];
 #pragma unroll
-        for (int t = 0; t < 4; t++) {
-          const uint32_t j = 32u * (4 * g + t) + lane;
-          const uint64_t a0 = (w == 0) ? 0ull : rot_read(lut, j, rot);
-          const uint64_t a1 = (w == 0) ? 0ull : rot_read(lut, j + 1024u, rot);
-          v[4 * t] = (uint32_t)a0; v[4 * t + 1] = (uint32_t)(a0 >> 32);
-          v[4 * t + 2] = (uint32_t)a1; v[4 * t + 3] = (uint32_t)(a1 >> 32);
-          shp[j] = shadow_word(a0);
-          shp[j + 1024u] = shadow_word(a1);
+        for (int t = 0; t < 8; t++) {
+          const uint32_t j = 32u * (8 * g + t) + lane;
+          v[2 * t] = (w == 0) ? 0u : (uint32_t)(rot_read(lut, j, rot) >> 32);
+          v[2 * t + 1] = (w == 0) ? 0u : (uint32_t)(rot_read(lut, j + 1024u, rot) >> 32);
+          shp[j] = v[2 * t];
+          shp[j + 1024u] = v[2 * t + 1];
         }
         tmem_st16(tacc + 16 * g, v);
       }
@@ -288,23 +287,21 @@ blind_rotate_kernel(const c2* __restrict__ fbsk, const uint64_t* __restrict__ sm
       row_store(xi, plane + pp * kHalfN, k1);
       bar_sync(bar_id, 64);
       col_load_brev(xi, plane + w * kHalfN, lane);
-      // phase C: inverse pass 2 -> untwist, round to torus, accumulate into TMEM, refresh the shadow
+      // phase C: inverse pass 2 -> untwist, round to the 32-bit torus, accumulate (TMEM copy + shared copy)
       fft32_inv(xr, xi);
 #pragma unroll
-      for (int g = 0; g < 8; g++) {
+      for (int g = 0; g < 4; g++) {
         uint32_t v[16];
         tmem_ld16(tacc + 16 * g, v);
 #pragma unroll
-        for (int t = 0; t < 4; t++) {
-          const int r = 4 * g + t;
-          uint64_t inc0, inc1;
-          phaseC_increments(xr, xi, r, inc0, inc1);
-          const uint64_t a0 = (((uint64_t)v[4 * t + 1] << 32) | v[4 * t]) + inc0;
-          const uint64_t a1 = (((uint64_t)v[4 * t + 3] << 32) | v[4 * t + 2]) + inc1;
-          v[4 * t] = (uint32_t)a0; v[4 * t + 1] = (uint32_t)(a0 >> 32);
-          v[4 * t + 2] = (uint32_t)a1; v[4 * t + 3] = (uint32_t)(a1 >> 32);
-          shp[32 * r + lane] = shadow_word(a0);
-          shp[32 * r + lane + 1024] = shadow_word(a1);
+        for (int t = 0; t < 8; t++) {
+          const int r = 8 * g + t;
+          uint32_t inc0, inc1;
+          phaseC_increments32(xr, xi, r, inc0, inc1);
+          v[2 * t] += inc0;
+          v[2 * t + 1] += inc1;
+          shp[32 * r + lane] = v[2 * t];
+          shp[32 * r + lane + 1024] = v[2 * t + 1];
         }
         tmem_st16(tacc + 16 * g, v);
       }
@@ -316,22 +313,13 @@ blind_rotate_kernel(const c2* __restrict__ fbsk, const uint64_t* __restrict__ sm
     {
       const size_t row = out_rows ? (size_t)out_rows[sample] : (size_t)sample;
       uint64_t* o = out + row * kBig;
-#pragma unroll 1
-      for (int g = 0; g < 8; g++) {
-        uint32_t v[16];
-        tmem_ld16(tacc + 16 * g, v);
-#pragma unroll
-        for (int t = 0; t < 4; t++) {
-          const uint32_t j = 32u * (4 * g + t) + lane;
-          const uint64_t a0 = ((uint64_t)v[4 * t + 1] << 32) | v[4 * t];
-          const uint64_t a1 = ((uint64_t)v[4 * t + 3] << 32) | v[4 * t + 2];
-          if (w == 0) {
-            if (j == 0) o[0] = a0; else o[kN - j] = (uint64_t)0 - a0;
-            o[kN - (j + 1024u)] = (uint64_t)0 - a1;
-          } else if (j == 0) {
-            o[kN] = a0;
-          }
+      if (w == 0) {
+        for (int j = lane; j < kN; j += 32) {
+          const uint32_t v = (j == 0) ? shp[0] : 0u - shp[kN - j];
+          o[j] = (uint64_t)v << 32;
         }
+      } else if (lane == 0) {
+        o[kN] = (uint64_t)shp[0] << 32;
       }
     }
   }

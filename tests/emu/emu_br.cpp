@@ -13,8 +13,8 @@ struct Regs { double xr[32], xi[32]; };
 
 struct Sample {
   std::vector<uint64_t> acc;   // [2][2048] (only used by the product check)
-  std::vector<uint32_t> shadow; // [2][2048] 32-bit shadow accumulator (shared memory on the device)
-  uint64_t master[2][32][64];  // [warp][lane][2r + half]: thread-private 64-bit accumulator (tensor memory on the device)
+  std::vector<uint32_t> shadow; // [2][2048] 32-bit accumulator, shared copy (rotation reads of the decomposition)
+  uint32_t master[2][32][64];  // [warp][lane][2r + half]: thread-private copy of the same words (tensor memory on the device)
   std::vector<double> plane;   // [2][1024]: the re and the im planes pass through it one after the other
   Regs regs[2][32];            // [warp][lane]
   Sample() : acc(2 * kN), shadow(2 * kN), plane(2 * kHalfN) {}
@@ -109,14 +109,14 @@ static void cmux_step(Sample& s, const c2* fbsk, int i, uint32_t a) {
   for (int w = 0; w < 2; w++)
     for (int lane = 0; lane < 32; lane++)
       for (int r = 0; r < 32; r++) {
-        uint64_t inc0, inc1;
-        phaseC_increments(s.regs[w][lane].xr, s.regs[w][lane].xi, r, inc0, inc1);
-        uint64_t& a0 = s.master[w][lane][2 * r];
-        uint64_t& a1 = s.master[w][lane][2 * r + 1];
+        uint32_t inc0, inc1;
+        phaseC_increments32(s.regs[w][lane].xr, s.regs[w][lane].xi, r, inc0, inc1);
+        uint32_t& a0 = s.master[w][lane][2 * r];
+        uint32_t& a1 = s.master[w][lane][2 * r + 1];
         a0 += inc0;
         a1 += inc1;
-        s.shadow[w * kN + 32 * r + lane] = shadow_word(a0);
-        s.shadow[w * kN + 32 * r + lane + 1024] = shadow_word(a1);
+        s.shadow[w * kN + 32 * r + lane] = a0;
+        s.shadow[w * kN + 32 * r + lane + 1024] = a1;
       }
 }
 
@@ -130,9 +130,9 @@ extern "C" void emu_blind_rotate(const c2* fbsk, const uint64_t* small, const ui
       for (int r = 0; r < 32; r++)
         for (int h = 0; h < 2; h++) {
           const int j = 32 * r + lane + 1024 * h;
-          const uint64_t v = w == 0 ? 0ull : rot_read(lut, j, (4096u - bt) & 4095u);
+          const uint32_t v = w == 0 ? 0u : (uint32_t)(rot_read(lut, j, (4096u - bt) & 4095u) >> 32);
           s.master[w][lane][2 * r + h] = v;
-          s.shadow[w * kN + j] = shadow_word(v);
+          s.shadow[w * kN + j] = v;
         }
   const int steps = max_steps < 0 ? kLweN : max_steps;
   for (int i = 0; i < steps; i++) {
@@ -143,7 +143,7 @@ extern "C" void emu_blind_rotate(const c2* fbsk, const uint64_t* small, const ui
   for (int w = 0; w < 2; w++)
     for (int lane = 0; lane < 32; lane++)
       for (int r = 0; r < 32; r++)
-        for (int h = 0; h < 2; h++) acc_out[w * kN + 32 * r + lane + 1024 * h] = s.master[w][lane][2 * r + h];
+        for (int h = 0; h < 2; h++) acc_out[w * kN + 32 * r + lane + 1024 * h] = (uint64_t)s.master[w][lane][2 * r + h] << 32;
   delete &s;
 }
 
