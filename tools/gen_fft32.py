@@ -52,6 +52,19 @@ def lit(x):
     return repr(float(x))
 
 
+KTAB = []  # distinct |constants| of the butterflies; referenced as FBK(i) so that the device code reads them
+           # straight out of the constant bank as DFMA operands (literals cost two UMOVs per use)
+
+
+def kref(x):
+    x = float(x)
+    a = abs(x)
+    if a not in KTAB:
+        KTAB.append(a)
+    r = "FBK(%d)" % KTAB.index(a)
+    return "-" + r if x < 0 else r
+
+
 class Emitter:
     """Tracks, per array slot, stored value -> true value = sign * mag * stored (sign per component)."""
 
@@ -109,7 +122,7 @@ class Emitter:
             return f"{y} + {x}"
         if kf == -1.0:
             return f"{y} - {x}"
-        return f"fb_fma({x}, {lit(kf)}, {y})"
+        return f"fb_fma({x}, {kref(kf)}, {y})"
 
     def butterfly(self, a, b):
         """(a, b) <- (a + b, a - b) in true values; results inherit a's pending magnitude and signs."""
@@ -150,7 +163,7 @@ def gen_dit(sign, slot_of_pos, twist):
 
 def replay(lines, xr, xi):
     """execute the emitted C statements with numpy float64 semantics (fma -> separate mul/add: fine for a check)"""
-    env = {"xr": xr, "xi": xi, "fb_fma": lambda a, b, c: a * b + c}
+    env = {"xr": xr, "xi": xi, "fb_fma": lambda a, b, c: a * b + c, "FBK": lambda i: KTAB[i]}
     for ln in lines:
         body = ln.strip()
         assert body.startswith("{") and body.endswith("}")
@@ -199,6 +212,7 @@ def main():
     out.append("")
     # forward: natural input index r sits in array slot r; position p holds x[brev5(p)] -> slot brev5(p);
     # output X[k] ends at position k = slot brev5(k): "register q holds X[brev5(q)]"
+    body = []
     fwd_slot = brev5
     # inverse: slot q holds Y[brev5(q)] = the input of position q; output natural: y[n] at slot n
     inv_slot = lambda p: p
@@ -207,11 +221,25 @@ def main():
         E = gen_dit(sign, slot, twist)
         err = check(E, sign, slot, twist, outslot)
         print(f"{name}: {E.slots} FP64 slots, replay max err {err:.2e}")
-        out.append(f"// {E.slots} FP64 issue slots")
-        out.append(f"FB_HD void {name}(double (&xr)[32], double (&xi)[32]) {{")
-        out += ["  " + l for l in E.lines]
-        out.append("}")
-        out.append("")
+        body.append(f"// {E.slots} FP64 issue slots")
+        body.append(f"FB_HD void {name}(double (&xr)[32], double (&xi)[32]) {{")
+        body += ["  " + l for l in E.lines]
+        body.append("}")
+        body.append("")
+    out.append("// butterfly constants (tangents and magnitude ratios); device code reads them from the constant bank")
+    out.append("#define FB_KTAB_INIT { " + ", ".join(lit(k) for k in KTAB) + " }")
+    out.append("#if defined(__CUDACC__)")
+    out.append(f"static __constant__ double fb_ktab_d[{len(KTAB)}] = FB_KTAB_INIT;")
+    out.append("#endif")
+    out.append(f"static const double fb_ktab_h[{len(KTAB)}] = FB_KTAB_INIT;")
+    out.append("#if defined(__CUDA_ARCH__)")
+    out.append("#define FBK(i) fb_ktab_d[i]")
+    out.append("#else")
+    out.append("#define FBK(i) fb_ktab_h[i]")
+    out.append("#endif")
+    out.append("")
+    out += body
+    print(len(KTAB), "distinct constants")
     with open(OUT, "w") as f:
         f.write("\n".join(out) + "\n")
     print("wrote", os.path.normpath(OUT), len(out), "lines")
