@@ -76,7 +76,8 @@ extern "C" void fb_ctx_destroy(fb_ctx* ctx) {
   cudaFree(ctx->d_kb);
   cudaFree(ctx->d_fbsk);
   cudaFree(ctx->d_tabs);
-  for (fb_devbuf* b : {&ctx->in, &ctx->small, &ctx->out, &ctx->luts, &ctx->lut_idx, &ctx->digits}) cudaFree(b->p);
+  for (fb_devbuf* b : {&ctx->in, &ctx->small, &ctx->out, &ctx->luts, &ctx->lut_idx, &ctx->digits, &ctx->arena, &ctx->plan_i32,
+                       &ctx->plan_i64, &ctx->plan_u64, &ctx->plan_u32, &ctx->regex_luts}) cudaFree(b->p);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

@@ -28,6 +28,9 @@ struct fb_ctx {
   bool have_key = false;
   // scratch for the batch entry points
   fb_devbuf in, small, out, luts, lut_idx, digits;
+  // has_match: arena of ciphertext rows, flattened plan arrays, the fixed accumulator table (uploaded once)
+  fb_devbuf arena, plan_i32, plan_i64, plan_u64, plan_u32, regex_luts;
+  bool regex_luts_ready = false;
   // timing
   bool timing = false;
   std::vector<fb_event_pair> pending;

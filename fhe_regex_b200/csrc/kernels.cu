@@ -407,6 +407,16 @@ static cudaError_t launch_br_s(const c2* fbsk, const uint64_t* small, const uint
 cudaError_t launch_blind_rotate(const c2* fbsk, const uint64_t* small, const uint64_t* luts, const uint32_t* lut_idx,
                                 uint64_t* out, const int32_t* out_rows, const c2* tabs, int count, cudaStream_t st) {
   if (count <= 0) return cudaSuccess;
+  // Throughput wants 4 samples per SM; a batch that does not fill the GPU at that width (the narrow DAG
+  // levels of a regex match) finishes sooner with fewer samples contending for each SM.
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  if (count <= sms) return launch_br_s<1>(fbsk, small, luts, lut_idx, out, out_rows, tabs, count, st);
+  if (count <= 2 * sms) return launch_br_s<2>(fbsk, small, luts, lut_idx, out, out_rows, tabs, count, st);
+  if (count <= 3 * sms) return launch_br_s<3>(fbsk, small, luts, lut_idx, out, out_rows, tabs, count, st);
   return launch_br_s<4>(fbsk, small, luts, lut_idx, out, out_rows, tabs, count, st);
 }
 

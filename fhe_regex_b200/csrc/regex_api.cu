@@ -40,19 +40,6 @@ void flatten_plan(const Plan& plan, DevPlan& d) {
   }
 }
 
-struct ScopedDev {
-  std::vector<void*> ptrs;
-  ~ScopedDev() { for (void* p : ptrs) cudaFree(p); }
-  template <class T>
-  cudaError_t alloc(T** out, size_t n) {
-    void* p = nullptr;
-    cudaError_t e = cudaMalloc(&p, (n ? n : 1) * sizeof(T));
-    if (e == cudaSuccess) ptrs.push_back(p);
-    *out = (T*)p;
-    return e;
-  }
-};
-
 // fixed accumulator table (shortint generate_accumulator layout), LutId order
 void build_lut_table(std::vector<uint64_t>& luts) {
   luts.resize((size_t)LUT_COUNT * FB_POLY_SIZE);
@@ -79,20 +66,21 @@ int run_plan(fb_ctx* ctx, const Plan& plan, const uint64_t* h_in, size_t n_in_ro
   FB_CUDA(ctx, cudaSetDevice(ctx->device));
   DevPlan d;
   flatten_plan(plan, d);
-  ScopedDev dev;
-  uint64_t *d_arena = nullptr, *d_u64 = nullptr, *d_luts = nullptr, *d_small = nullptr;
-  int32_t* d_i32 = nullptr;
-  int64_t* d_i64 = nullptr;
-  uint32_t* d_u32 = nullptr;
-  std::vector<uint64_t> luts;
-  build_lut_table(luts);
-  FB_CUDA(ctx, dev.alloc(&d_arena, (size_t)plan.n_rows * FB_LWE_BIG_WORDS));
-  FB_CUDA(ctx, dev.alloc(&d_small, (size_t)(plan.stats.max_level_width + 1) * FB_LWE_SMALL_WORDS));
-  FB_CUDA(ctx, dev.alloc(&d_i32, d.i32.size()));
-  FB_CUDA(ctx, dev.alloc(&d_i64, d.i64.size()));
-  FB_CUDA(ctx, dev.alloc(&d_u64, d.u64.size()));
-  FB_CUDA(ctx, dev.alloc(&d_u32, d.u32.size()));
-  FB_CUDA(ctx, dev.alloc(&d_luts, luts.size()));
+  int rc;
+  if ((rc = fb_reserve(ctx, ctx->arena, (size_t)plan.n_rows * FB_LWE_BIG_WORDS * 8))) return rc;
+  if ((rc = fb_reserve(ctx, ctx->small, (size_t)(plan.stats.max_level_width + 1) * FB_LWE_SMALL_WORDS * 8))) return rc;
+  if ((rc = fb_reserve(ctx, ctx->plan_i32, (d.i32.size() + 1) * 4))) return rc;
+  if ((rc = fb_reserve(ctx, ctx->plan_i64, (d.i64.size() + 1) * 8))) return rc;
+  if ((rc = fb_reserve(ctx, ctx->plan_u64, (d.u64.size() + 1) * 8))) return rc;
+  if ((rc = fb_reserve(ctx, ctx->plan_u32, (d.u32.size() + 1) * 4))) return rc;
+  if ((rc = fb_reserve(ctx, ctx->regex_luts, (size_t)LUT_COUNT * FB_POLY_SIZE * 8))) return rc;
+  uint64_t* d_arena = (uint64_t*)ctx->arena.p;
+  uint64_t* d_small = (uint64_t*)ctx->small.p;
+  int32_t* d_i32 = (int32_t*)ctx->plan_i32.p;
+  int64_t* d_i64 = (int64_t*)ctx->plan_i64.p;
+  uint64_t* d_u64 = (uint64_t*)ctx->plan_u64.p;
+  uint32_t* d_u32 = (uint32_t*)ctx->plan_u32.p;
+  uint64_t* d_luts = (uint64_t*)ctx->regex_luts.p;
   cudaStream_t st = ctx->stream;
   cudaEvent_t ev0, ev1;
   FB_CUDA(ctx, cudaEventCreate(&ev0));
@@ -108,7 +96,13 @@ int run_plan(fb_ctx* ctx, const Plan& plan, const uint64_t* h_in, size_t n_in_ro
   RP_CUDA(cudaMemcpyAsync(d_i64, d.i64.data(), d.i64.size() * 8, cudaMemcpyHostToDevice, st));
   RP_CUDA(cudaMemcpyAsync(d_u64, d.u64.data(), d.u64.size() * 8, cudaMemcpyHostToDevice, st));
   RP_CUDA(cudaMemcpyAsync(d_u32, d.u32.data(), d.u32.size() * 4, cudaMemcpyHostToDevice, st));
-  RP_CUDA(cudaMemcpyAsync(d_luts, luts.data(), luts.size() * 8, cudaMemcpyHostToDevice, st));
+  if (!ctx->regex_luts_ready) {   // the accumulator table is fixed: upload it once per context
+    std::vector<uint64_t> luts;
+    build_lut_table(luts);
+    RP_CUDA(cudaMemcpyAsync(d_luts, luts.data(), luts.size() * 8, cudaMemcpyHostToDevice, st));
+    RP_CUDA(cudaStreamSynchronize(st));
+    ctx->regex_luts_ready = true;
+  }
   RP_CUDA(cudaEventRecord(ev0, st));
   for (auto& o : d.levels) {
     int rc;
