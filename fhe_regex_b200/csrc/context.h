@@ -2,10 +2,14 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <memory>
 #include <string>
+#include <utility>
 #include <vector>
 #include "../../include/fhe_b200.h"
 #include "kernels.h"
+
+namespace fbre { struct Plan; }
 
 struct fb_devbuf {
   void* p = nullptr;
@@ -31,6 +35,9 @@ struct fb_ctx {
   // has_match: arena of ciphertext rows, flattened plan arrays, the fixed accumulator table (uploaded once)
   fb_devbuf arena, plan_i32, plan_i64, plan_u64, plan_u32, regex_luts;
   bool regex_luts_ready = false;
+  // lowered plans of recent (pattern, content length, rank, world) requests: the plan depends on nothing else, so a
+  // server matching many contents against one pattern builds it once (most recent first, at most 8)
+  std::vector<std::pair<std::string, std::shared_ptr<const fbre::Plan>>> plan_cache;
   // timing
   bool timing = false;
   std::vector<fb_event_pair> pending;

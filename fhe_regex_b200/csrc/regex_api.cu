@@ -4,7 +4,10 @@
 //
 // Replaces has_match (engine.rs:8-42) + Execution (execution.rs:37-223) of the reference.
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <cstring>
+#include <memory>
+#include <string>
 #include <vector>
 #include "context.h"
 #include "regex_host.h"
@@ -166,15 +169,28 @@ extern "C" int fb_plan_eval_plain(const char* pattern, const uint8_t* content, s
 extern "C" int fb_has_match_shard(fb_ctx* ctx, const uint64_t* h_content, size_t n_chars, const char* pattern, int rank,
                                   int world, uint64_t* h_out, fb_match_stats* stats) {
   if (!ctx || !pattern || !h_out || (!h_content && n_chars)) return fb_fail(ctx, FB_ERR_ARG, "null argument");
-  Plan plan;
-  std::string err;
-  int rc = build_plan(pattern, n_chars, rank, world, plan, err);
-  if (rc != FB_OK) return fb_fail(ctx, rc, err);
+  const std::string key = std::string(pattern) + '\n' + std::to_string(n_chars) + '/' + std::to_string(rank) + '/' + std::to_string(world);
+  std::shared_ptr<const Plan> plan;
+  for (size_t i = 0; i < ctx->plan_cache.size(); i++)
+    if (ctx->plan_cache[i].first == key) {
+      plan = ctx->plan_cache[i].second;
+      std::rotate(ctx->plan_cache.begin(), ctx->plan_cache.begin() + i, ctx->plan_cache.begin() + i + 1);
+      break;
+    }
+  if (!plan) {
+    auto fresh = std::make_shared<Plan>();
+    std::string err;
+    int rc = build_plan(pattern, n_chars, rank, world, *fresh, err);
+    if (rc != FB_OK) return fb_fail(ctx, rc, err);
+    plan = fresh;
+    ctx->plan_cache.insert(ctx->plan_cache.begin(), std::make_pair(key, plan));
+    if (ctx->plan_cache.size() > 8) ctx->plan_cache.pop_back();
+  }
   double ms = 0;
-  rc = run_plan(ctx, plan, h_content, 4 * n_chars, h_out, &ms);
+  int rc = run_plan(ctx, *plan, h_content, 4 * n_chars, h_out, &ms);
   if (rc != FB_OK) return rc;
   if (stats) {
-    *stats = plan.stats;
+    *stats = plan->stats;
     stats->gpu_ms = ms;
   }
   return FB_OK;

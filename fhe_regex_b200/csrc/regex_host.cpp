@@ -375,7 +375,7 @@ struct Res { int32_t val, key; };
 
 struct Execution {
   Interner keys, vals;
-  std::unordered_map<int32_t, int32_t> cache;  // key -> value (HashMap<Executed, RadixCiphertext>)
+  std::vector<int32_t> cache;  // key id -> value id or -1 (HashMap<Executed, RadixCiphertext>)
   uint64_t ct_ops = 0, cache_hits = 0, calls = 0;
   uint64_t by_type[8] = {0};
 
@@ -418,15 +418,15 @@ struct Execution {
   template <class F>
   Res with_cache(int32_t key, int type, F f) {  // execution.rs:212-222
     calls++;
-    auto it = cache.find(key);
-    if (it != cache.end()) {
+    if ((size_t)key >= cache.size()) cache.resize(std::max<size_t>((size_t)key + 1, cache.size() * 2), -1);
+    if (cache[key] >= 0) {
       cache_hits++;
-      return Res{it->second, key};
+      return Res{cache[key], key};
     }
     ct_ops++;
     by_type[type]++;
     int32_t v = f();
-    cache.emplace(key, v);
+    cache[key] = v;
     return Res{v, key};
   }
   Res ct_eq(Res a, Res b) { return with_cache(keys.get(K_EQ, a.key, b.key), K_EQ, [&] { return v_cmp(V_EQ, a.val, b.val); }); }
@@ -531,13 +531,17 @@ struct Lowering {
   size_t n;
   std::vector<PbsNode> nodes;
   std::map<std::vector<int64_t>, int32_t> node_memo;      // canonical (lut, const, terms) -> node
-  std::unordered_map<int32_t, LitOrConst> lowered;          // value id -> literal
+  std::vector<LitOrConst> lowered;                          // value id -> literal (kind -1: not lowered yet)
+  std::vector<uint32_t> seen_stamp;                         // flattening scratch: value id -> generation
+  uint32_t seen_gen = 0;
   std::map<std::vector<int64_t>, int32_t> shape_intern;    // shift-invariant structure -> shape id
   std::unordered_map<int32_t, std::pair<int32_t, int32_t>> node_shape;  // PBS node -> (shape, base position)
   std::map<int32_t, std::map<int32_t, int32_t>> shape_nodes;           // shape -> base position -> PBS node
   std::map<std::vector<int64_t>, Lit> run_memo;             // (shape, neg, start, len) -> literal of the AND over the run
 
-  Lowering(Execution& e, size_t n_chars) : ex(e), n(n_chars) {}
+  Lowering(Execution& e, size_t n_chars)
+      : ex(e), n(n_chars), lowered(e.vals.items.size(), LitOrConst{-1, {0, false}}), seen_stamp(e.vals.items.size(), 0) {}
+  bool is_lowered(int32_t v) const { return lowered[v].kind >= 0; }
 
   int level_of(int32_t ref) const { return ref < 0 ? 0 : nodes[ref].level; }
 
@@ -643,7 +647,7 @@ struct Lowering {
     std::vector<int32_t> stack{root};
     while (!stack.empty()) {
       const int32_t v = stack.back();
-      if (lowered.count(v)) { stack.pop_back(); continue; }
+      if (is_lowered(v)) { stack.pop_back(); continue; }
       const Triple t = ex.vals.items[v];
       if (t.t == V_CONST) { lowered[v] = LitOrConst{t.a & 1, {0, false}}; stack.pop_back(); continue; }
       if (t.t == V_EQ) {  // eq = [e_lo + e_hi == 2]
@@ -664,7 +668,7 @@ struct Lowering {
         continue;
       }
       if (t.t == V_NOT) {
-        if (!lowered.count(t.a)) { stack.push_back(t.a); continue; }
+        if (!is_lowered(t.a)) { stack.push_back(t.a); continue; }
         LitOrConst a = lowered[t.a];
         if (a.kind < 2) lowered[v] = LitOrConst{a.kind ^ 1, {0, false}};
         else lowered[v] = LitOrConst{2, Lit{a.lit.node, !a.lit.neg}};
@@ -675,37 +679,45 @@ struct Lowering {
       std::vector<int32_t> ops, work{t.a, t.b};
       bool missing = false;
       {
-        std::vector<int32_t> seen_stack;
-        std::unordered_map<int32_t, bool> seen;
+        seen_gen++;
         while (!work.empty()) {
           int32_t x = work.back();
           work.pop_back();
-          if (seen.count(x)) continue;
-          seen[x] = true;
+          if (seen_stamp[x] == seen_gen) continue;
+          seen_stamp[x] = seen_gen;
           const Triple tx = ex.vals.items[x];
           if (tx.t == t.t) { work.push_back(tx.a); work.push_back(tx.b); continue; }
           ops.push_back(x);
-          if (!lowered.count(x)) { stack.push_back(x); missing = true; }
+          if (!is_lowered(x)) { stack.push_back(x); missing = true; }
         }
       }
       if (missing) continue;
       const bool is_and = t.t == V_AND;
       std::vector<Lit> lits;
       bool decided = false;
-      std::sort(ops.begin(), ops.end());
-      std::map<int32_t, int> polarity;  // node -> bitmask of polarities seen
+      // operand literals: drop neutral constants, dedupe (idempotence), detect x & !x / x | !x
       for (int32_t x : ops) {
-        LitOrConst lx = lowered[x];
+        const LitOrConst& lx = lowered[x];
         if (lx.kind < 2) {
-          if ((lx.kind == 0) == is_and) { lowered[v] = LitOrConst{is_and ? 0 : 1, {0, false}}; decided = true; break; }
-          continue;  // neutral element
+          if ((lx.kind == 0) == is_and) { decided = true; break; }  // absorbing element
+          continue;                                                 // neutral element
         }
-        int& pm = polarity[lx.lit.node];
-        const int bit = lx.lit.neg ? 2 : 1;
-        if (pm & bit) continue;             // idempotent
-        pm |= bit;
-        if (pm == 3) { lowered[v] = LitOrConst{is_and ? 0 : 1, {0, false}}; decided = true; break; }  // x & !x, x | !x
         lits.push_back(lx.lit);
+      }
+      if (decided) {
+        lowered[v] = LitOrConst{is_and ? 0 : 1, {0, false}};
+      } else {
+        std::sort(lits.begin(), lits.end(), [](const Lit& x, const Lit& y) { return x.node < y.node || (x.node == y.node && x.neg < y.neg); });
+        size_t o = 0;
+        for (size_t i2 = 0; i2 < lits.size(); i2++) {
+          if (o > 0 && lits[o - 1].node == lits[i2].node) {
+            if (lits[o - 1].neg != lits[i2].neg) { decided = true; break; }  // both polarities of one node
+            continue;                                                       // duplicate
+          }
+          lits[o++] = lits[i2];
+        }
+        if (decided) lowered[v] = LitOrConst{is_and ? 0 : 1, {0, false}};
+        else lits.resize(o);
       }
       if (decided) { stack.pop_back(); continue; }
       if (lits.empty()) { lowered[v] = LitOrConst{is_and ? 1 : 0, {0, false}}; stack.pop_back(); continue; }
