@@ -180,3 +180,16 @@ def test_errors_surface_like_the_reference(fck, gpu_key):
         fb.has_match(gpu_key, ct, "/a(b/")
     with pytest.raises(fb.ReferencePanic):
         fb.has_match(gpu_key, ct, "/^/")
+
+
+def test_bootstrap_noise_many_trials():
+    """North-star criterion: no decryption failure and output noise within the bound over 10^6 fresh
+    encryptions (about half a minute on a B200 box; FB_NOISE_TRIALS overrides).  A recorded run is in
+    profiles/r01_noise_1e6_trials.json."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("noise_trials", os.path.join(os.path.dirname(__file__), "..", "tools", "noise_trials.py"))
+    nt = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(nt)
+    res = nt.run(int(os.environ.get("FB_NOISE_TRIALS", "1000000")))
+    assert res["decryption_failures"] == 0, res
+    assert res["err_std"] < PBS_ERR_STD_MAX and res["err_abs_max"] < PBS_ERR_MAX, res

@@ -1,0 +1,69 @@
+#!/usr/bin/env python3
+"""Bootstrap correctness / noise over many trials on the GPU (north-star criterion: no decryption failure
+across >= 10^6 trials, output-noise variance within the parameter set's bound).
+
+    python tools/noise_trials.py [trials] [--json out.json]
+
+Every trial is a fresh encryption (own mask, own Gaussian noise) of a uniform 4-bit message, bootstrapped
+through a LUT drawn from the has_match table plus identity / affine LUTs.  Outputs are decrypted on the CPU
+with the fixture secret key; the phase error against the expected plaintext is accumulated."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import fhe_regex_b200 as fb  # noqa: E402
+
+
+def run(trials: int, chunk: int = 28416, seed: int = 2026):
+    ck = fb.ClientKey.load(os.path.join(ROOT, "tests", "golden", "client_key"))
+    ksk, bsk = fb.keygen_server_raw(ck, seed=0)
+    sk = fb.ServerKey(ksk, bsk)
+    fs = [lambda x: x, lambda x: (5 * x + 3) % 16, lambda x: int(x == 7), lambda x: int(x >= 1), lambda x: int(x > 9), lambda x: 15 - x,
+          lambda x: int(x == 2), lambda x: int(x < 2)]
+    luts = np.stack([fb.make_lut(f) for f in fs])
+    tab = np.array([[f(m) & 15 for m in range(16)] for f in fs], dtype=np.uint64)
+    key = ck.big.astype(np.uint64)
+    rng = np.random.default_rng(seed)
+    done = fails = 0
+    s1 = s2 = 0.0
+    amax = 0.0
+    t0 = time.time()
+    gpu_s = 0.0
+    while done < trials:
+        n = min(chunk, trials - done)
+        msgs = rng.integers(0, 16, size=n)
+        idx = rng.integers(0, len(fs), size=n).astype(np.uint32)
+        cts = ck.encrypt_blocks(msgs, seed=seed + 1, stream0=done)     # fresh mask + noise per trial
+        tg = time.time()
+        out = sk.pbs(cts, luts, idx)
+        gpu_s += time.time() - tg
+        exp = tab[idx, msgs]
+        with np.errstate(over="ignore"):
+            phase = out[:, 2048] - (out[:, :2048] * key[None, :]).sum(axis=1, dtype=np.uint64)
+            dec = ((phase + np.uint64(1 << 58)) >> np.uint64(59)) & np.uint64(15)
+            err = (phase - (exp << np.uint64(59))).view(np.int64).astype(np.float64) / 2.0 ** 64
+        fails += int((dec != exp).sum())
+        s1 += float(err.sum())
+        s2 += float((err * err).sum())
+        amax = max(amax, float(np.abs(err).max()))
+        done += n
+    sk.close()
+    mean = s1 / done
+    var = s2 / done - mean * mean
+    return {"trials": done, "decryption_failures": fails, "err_mean": mean, "err_std": var ** 0.5, "err_var": var, "err_abs_max": amax,
+            "expected_std_bound": 3.7e-5, "half_box": 1.0 / 32, "wall_s": time.time() - t0, "pbs_call_s": gpu_s}
+
+
+if __name__ == "__main__":
+    trials = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 1000000
+    res = run(trials)
+    print(json.dumps(res))
+    if "--json" in sys.argv:
+        with open(sys.argv[sys.argv.index("--json") + 1], "w") as f:
+            json.dump(res, f, indent=1)
+    sys.exit(1 if res["decryption_failures"] else 0)
