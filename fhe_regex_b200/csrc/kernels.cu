@@ -75,6 +75,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// whole-warp wait: the exit condition is a vote, so the warp provably leaves the loop converged (a per-thread
+// exit makes ptxas wrap every later shuffle in WARPSYNC.COLLECTIVE / ENDCOLLECTIVE with register moves)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done;
@@ -84,7 +86,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(done)
         : "r"(addr), "r"(parity)
         : "memory");
-  } while (!done);
+  } while (!__all_sync(0xffffffffu, done));
 }
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
@@ -245,11 +247,13 @@ blind_rotate_kernel(const c2* __restrict__ fbsk, const uint64_t* __restrict__ sm
     const c2* b_in = stage + ((size_t)((1 - pp) * 2 + pp) * kHalfN + k1);   // GGSW[row 1-pp][column pp]
     uint32_t n_exec = 0;
     for (int i = 0; i < kLweN; i++) {
-      if (!need[i]) continue;  // CTA-uniform: zero mask element (trivial inputs) or X^0 for every sample
+      // CTA-uniform: zero mask element (trivial inputs) or X^0 for every sample.  The votes only tell the
+      // compiler what is true anyway: these branches are warp-uniform.
+      if (!__any_sync(0xffffffffu, need[i] != 0)) continue;
       const uint32_t a = at[i];
       const uint32_t par = n_exec & 1u;
       n_exec++;
-      if (!(a & 0x8000u)) {   // this sample skips the step, but still takes part in the hand-over
+      if (!__any_sync(0xffffffffu, (a & 0x8000u) != 0)) {   // this sample skips the step, but still takes part in the hand-over
         mbar_wait(full_bar, par);
         release_stage(i);
         continue;
