@@ -262,14 +262,14 @@ blind_rotate_kernel(const c2* __restrict__ fbsk, const uint64_t* __restrict__ sm
       phaseA_load32(xr, xi, shp, a & 4095u, lane);
       fft32_fwd_twist(xr, xi);
       fwd_twiddle_inplace(xr, xi, tab_f, lane);
-      bar_sync(bar_id, 64);                       // previous readers of the plane are done
-      col_store_brev(xr, plane + w * kHalfN, lane);
+      col_store_brev(xr, plane + w * kHalfN, lane);   // the plane is free: see the barrier after the last loads
       bar_sync(bar_id, 64);
       row_load(xr, plane + pp * kHalfN, k1);
       bar_sync(bar_id, 64);
       col_store_brev(xi, plane + w * kHalfN, lane);
       bar_sync(bar_id, 64);
       row_load(xi, plane + pp * kHalfN, k1);
+      bar_sync(bar_id, 64);                           // both warps have read: the next transpose may store at once
       // phase B: pass 2 -> Fourier MAC with the staged GGSW_i -> inverse pass 1 -> twiddle -> transpose
       fft32_fwd(xr, xi);
       mbar_wait(full_bar, par);
@@ -283,7 +283,6 @@ blind_rotate_kernel(const c2* __restrict__ fbsk, const uint64_t* __restrict__ sm
       release_stage(i);                           // this warp no longer reads the stage
       fft32_inv(xr, xi);
       inv_twiddle_inplace(xr, xi, tab_i, k1);
-      bar_sync(bar_id, 64);
       row_store(xr, plane + pp * kHalfN, k1);
       bar_sync(bar_id, 64);
       col_load_brev(xr, plane + w * kHalfN, lane);
@@ -291,6 +290,7 @@ blind_rotate_kernel(const c2* __restrict__ fbsk, const uint64_t* __restrict__ sm
       row_store(xi, plane + pp * kHalfN, k1);
       bar_sync(bar_id, 64);
       col_load_brev(xi, plane + w * kHalfN, lane);
+      bar_sync(bar_id, 64);
       // phase C: inverse pass 2 -> untwist, round to the 32-bit torus, accumulate (TMEM copy + shared copy)
       fft32_inv(xr, xi);
 #pragma unroll
