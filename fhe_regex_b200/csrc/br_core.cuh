@@ -13,11 +13,15 @@
 //   polynomial p (0 = GLWE mask, 1 = body), coefficient j in [0,2048)
 //   folded complex point z[j'] = (c[j'] + i c[j'+1024]) * exp(i*pi*j'/2048), j' = 32*r + lane
 //     -> thread `lane` of warp p holds register r = 0..31           (phase A / phase C)
-//   pass 1: in-register DFT over r        -> k1 (bit-reversed register order)
-//   twiddle exp(i*pi*lane*(1-4*k1)/2048), transpose through shared memory (XOR swizzle)
+//   pass 1: in-register DFT over r (fft32_fwd_twist, which also applies exp(i*pi*32r/2048)) -> k1
+//   twiddle exp(i*pi*lane*(1-4*k1)/2048) rebuilt from 4 "lo" x 8 "hi" factors, transpose through shared
+//   memory (XOR swizzle; the real and the imaginary plane one after the other)
 //   pass 2: thread (p', k1) holds c = 0..31, in-register DFT over c -> k2   (phase B)
 //     lanes 0-15 of warp w: p'=0, k1 = 16w + lane ; lanes 16-31: p'=1, k1 = 16w + lane - 16
 //   frequency index k = k1 + 32*k2, the Fourier bootstrapping key is stored in that natural order.
+//   The inverse runs the same two passes backwards with the conjugate twiddles.
+// Measured on B200: reading the twiddles from a 16 KiB shared-memory table or from
+// tensor memory is slower than the lo x hi rebuild -- shared-memory wavefronts are the scarce resource.
 #pragma once
 #include <stdint.h>
 #include <math.h>
@@ -72,38 +76,6 @@ FB_HD uint64_t rot_read(const uint64_t* accp, uint32_t j, uint32_t a) {
   uint32_t idx = (j - a) & 4095u;
   uint64_t v = accp[idx & 2047u];
   return (idx & 2048u) ? (uint64_t)0 - v : v;
-}
-
-// T5 decomposition, base 2^23 x 1 level: closest representable on the top 23 bits, balanced digit
-// in [-2^22+1, 2^22] (tie keeps +2^22, as tfhe-rs' decompose_one_level does).
-FB_HD double pbs_digit(uint64_t diff) {
-  uint32_t hi = (uint32_t)(diff >> 32);
-  uint32_t v = (((hi >> 8) + 1u) >> 1) & 0x7FFFFFu;
-  int32_t d = (v > 0x400000u) ? (int32_t)v - 0x800000 : (int32_t)v;
-  return (double)d;
-}
-
-// tfhe-rs from_torus: fractional part of t times 2^64 as a wrapping u64
-FB_HD uint64_t from_torus(double t) {
-#if defined(__CUDA_ARCH__)
-  double f = t - rint(t);
-  return (uint64_t)__double2ll_rn(f * 18446744073709551616.0);
-#else
-  double f = t - nearbyint(t);
-  double v = nearbyint(f * 18446744073709551616.0);
-  if (v >= 9223372036854775808.0) return 0x7fffffffffffffffull;
-  return (uint64_t)(int64_t)v;
-#endif
-}
-
-// ---- phase A: decompose (acc*X^a - acc) of polynomial accp into the folded FFT input (digits; untwisted) ----
-FB_HD void phaseA_load(double (&xr)[32], double (&xi)[32], const uint64_t* accp, uint32_t a, int lane) {
-#pragma unroll
-  for (int r = 0; r < 32; r++) {
-    const uint32_t j = 32u * r + lane;
-    xr[r] = pbs_digit(rot_read(accp, j, a) - accp[j]);
-    xi[r] = pbs_digit(rot_read(accp, j + 1024u, a) - accp[j + 1024u]);
-  }
 }
 
 // ---- 32-bit accumulator -------------------------------------------------------------------------
@@ -189,7 +161,7 @@ FB_HD void mac_point2(double& xr, double& xi, double pr, double pi, c2 b_own, c2
 
 // same folding (untwisted) for a standard-domain key polynomial read as a signed torus value in [-1/2, 1/2)
 // (key conversion K7; tfhe-rs forward_as_torus)
-FB_HD void phaseA_load_torus(double (&xr)[32], double (&xi)[32], const uint64_t* poly, int lane) {
+FB_HD void load_torus_poly(double (&xr)[32], double (&xi)[32], const uint64_t* poly, int lane) {
 #pragma unroll
   for (int r = 0; r < 32; r++) {
     const uint32_t j = 32u * r + lane;
@@ -198,95 +170,14 @@ FB_HD void phaseA_load_torus(double (&xr)[32], double (&xi)[32], const uint64_t*
   }
 }
 
-// after fft32_dif: register q holds k1 = brev5(q).  Multiply by exp(i*pi*lane*(1-4*k1)/2048)
-// (= tab[l][lane] * tab[4+h][lane], k1 = 4h + l) and store row k1, swizzled column lane^k1.
-FB_HD void fwd_twiddle_store(const double (&xr)[32], const double (&xi)[32], c2* tbuf_p, const c2* tab_f, int lane) {
-  c2 lo[4];
-#pragma unroll
-  for (int l = 0; l < 4; l++) lo[l] = tab_f[l * 32 + lane];
-#pragma unroll
-  for (int h = 0; h < 8; h++) {
-    const c2 hi = tab_f[(4 + h) * 32 + lane];
-#pragma unroll
-    for (int l = 0; l < 4; l++) {
-      const int k1 = 4 * h + l;
-      const int q = brev5(k1);
-      double tr = lo[l].x, ti = lo[l].y;
-      if (h != 0) {
-        tr = fb_fma(lo[l].x, hi.x, -(lo[l].y * hi.y));
-        ti = fb_fma(lo[l].x, hi.y, lo[l].y * hi.x);
-      }
-      c2 y;
-      y.x = fb_fma(xr[q], tr, -(xi[q] * ti));
-      y.y = fb_fma(xr[q], ti, xi[q] * tr);
-      tbuf_p[k1 * 32 + (lane ^ k1)] = y;
-    }
-  }
-}
-
-// ---- phase B: thread (pp, k1) loads its row c = 0..31 ----
-FB_HD void phaseB_load(double (&xr)[32], double (&xi)[32], const c2* tbuf_pp, int k1) {
-#pragma unroll
-  for (int c = 0; c < 32; c++) {
-    const c2 v = tbuf_pp[k1 * 32 + (c ^ k1)];
-    xr[c] = v.x;
-    xi[c] = v.y;
-  }
-}
-
-// Fourier-domain products of one frequency point with the "own" and the "other" output column
-FB_HD void mac_point(double xr, double xi, c2 b_own, c2 b_oth, double& keep_r, double& keep_i, double& send_r, double& send_i) {
-  keep_r = fb_fma(xr, b_own.x, -(xi * b_own.y));
-  keep_i = fb_fma(xr, b_own.y, xi * b_own.x);
-  send_r = fb_fma(xr, b_oth.x, -(xi * b_oth.y));
-  send_i = fb_fma(xr, b_oth.y, xi * b_oth.x);
-}
-
 // index (in complex elements) of Fourier GGSW element: [i][row pin][poly jout][k]
 FB_HD size_t fbsk_index(int i, int pin, int jout, int k) {
   return (((size_t)i * 2 + pin) * 2 + jout) * kHalfN + k;
 }
 
-// after fft32_dit_inv of phase B: register c holds column c.  Multiply by
-// exp(-i*pi*c*(1-4*k1)/2048) (= tab_i[l][k1] * tab_i[4+h][k1], c = 4h + l) and store row k1.
-FB_HD void inv_twiddle_store(const double (&xr)[32], const double (&xi)[32], c2* tbuf_pp, const c2* tab_i, int k1) {
-  c2 lo[4];
-#pragma unroll
-  for (int l = 0; l < 4; l++) lo[l] = tab_i[l * 32 + k1];
-#pragma unroll
-  for (int h = 0; h < 8; h++) {
-    const c2 hi = tab_i[(4 + h) * 32 + k1];
-#pragma unroll
-    for (int l = 0; l < 4; l++) {
-      const int c = 4 * h + l;
-      double tr = lo[l].x, ti = lo[l].y;
-      if (h != 0) {
-        tr = fb_fma(lo[l].x, hi.x, -(lo[l].y * hi.y));
-        ti = fb_fma(lo[l].x, hi.y, lo[l].y * hi.x);
-      }
-      c2 y;
-      y.x = fb_fma(xr[c], tr, -(xi[c] * ti));
-      y.y = fb_fma(xr[c], ti, xi[c] * tr);
-      tbuf_pp[k1 * 32 + (c ^ k1)] = y;
-    }
-  }
-}
-
-// ---- phase C: warp p, lane c loads column c in the bit-reversed register order fft32_dit_inv wants ----
-FB_HD void phaseC_load(double (&xr)[32], double (&xi)[32], const c2* tbuf_p, int lane) {
-#pragma unroll
-  for (int q = 0; q < 32; q++) {
-    const int k1 = brev5(q);
-    const c2 v = tbuf_p[k1 * 32 + (lane ^ k1)];
-    xr[q] = v.x;
-    xi[q] = v.y;
-  }
-}
-
 // ---- split transposes: the real and the imaginary planes go through one [2][1024] double buffer one
 // after the other (half the shared memory of a complex buffer; 4 two-warp barriers per transpose).
-// Same row/column swizzle as the complex versions: element (row k1, column c) of polynomial p lives at
-// p*1024 + k1*32 + (c ^ k1).
+// Element (row k1, column c) of polynomial p lives at p*1024 + k1*32 + (c ^ k1).
 
 // forward inter-pass twiddle in place: register q (row k1 = brev5(q)) *= exp(i*pi*lane*(1-4*k1)/2048)
 FB_HD void fwd_twiddle_inplace(double (&xr)[32], double (&xi)[32], const c2* tab_f, int lane) {
@@ -356,19 +247,6 @@ FB_HD void col_load_brev(double (&x)[32], const double* plane_p, int lane) {
   for (int q = 0; q < 32; q++) {
     const int k1 = brev5(q);
     x[q] = plane_p[k1 * 32 + (lane ^ k1)];
-  }
-}
-
-// untwist, scale by 1/1024, round to the torus and add into the accumulator polynomial
-FB_HD void phaseC_update(const double (&xr)[32], const double (&xi)[32], uint64_t* accp, int lane) {
-#pragma unroll
-  for (int r = 0; r < 32; r++) {
-    const double cr = fb_twist_cos(r) * (1.0 / 1024.0), sr = fb_twist_sin(r) * (1.0 / 1024.0);
-    const double re = fb_fma(xr[r], cr, xi[r] * sr);
-    const double im = fb_fma(xi[r], cr, -(xr[r] * sr));
-    const uint32_t j = 32u * r + lane;
-    accp[j] += from_torus(re);
-    accp[j + 1024u] += from_torus(im);
   }
 }
 

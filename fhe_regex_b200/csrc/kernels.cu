@@ -24,19 +24,24 @@ __device__ __forceinline__ void bar_sync(int id, int nthreads) {
 __global__ void __launch_bounds__(64, 1)
 bsk_convert_kernel(const uint64_t* __restrict__ bsk_std, c2* __restrict__ fbsk, const c2* __restrict__ tabs_g) {
   extern __shared__ __align__(16) unsigned char smem[];
-  c2* tbuf = reinterpret_cast<c2*>(smem);            // [2][1024]
-  c2* tab_f = tbuf + 2 * kHalfN;                      // [12][32]
+  double* plane = reinterpret_cast<double*>(smem);            // [2][1024]
+  c2* tab_f = reinterpret_cast<c2*>(plane + 2 * kHalfN);       // [12][32]
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
   for (int t = tid; t < kTabEntries * 32; t += 64) tab_f[t] = tabs_g[t];
   __syncthreads();
   const size_t row = blockIdx.x;  // (i * 2 + r)
   double xr[32], xi[32];
-  phaseA_load_torus(xr, xi, bsk_std + (row * 2 + w) * kN, lane);
+  load_torus_poly(xr, xi, bsk_std + (row * 2 + w) * kN, lane);
   fft32_fwd_twist(xr, xi);
-  fwd_twiddle_store(xr, xi, tbuf + w * kHalfN, tab_f, lane);
-  __syncthreads();
+  fwd_twiddle_inplace(xr, xi, tab_f, lane);
   const int pp = lane >> 4, k1 = 16 * w + (lane & 15);
-  phaseB_load(xr, xi, tbuf + pp * kHalfN, k1);
+  col_store_brev(xr, plane + w * kHalfN, lane);
+  __syncthreads();
+  row_load(xr, plane + pp * kHalfN, k1);
+  __syncthreads();
+  col_store_brev(xi, plane + w * kHalfN, lane);
+  __syncthreads();
+  row_load(xi, plane + pp * kHalfN, k1);
   fft32_fwd(xr, xi);
   c2* dst = fbsk + (row * 2 + pp) * kHalfN + k1;
 #pragma unroll
@@ -387,7 +392,7 @@ size_t br_smem_bytes(int S) {
 }
 
 cudaError_t launch_bsk_convert(const uint64_t* bsk_std, c2* fbsk, const c2* tabs, cudaStream_t st) {
-  const size_t smem = 2 * kHalfN * sizeof(c2) + kTabEntries * 32 * sizeof(c2);
+  const size_t smem = 2 * kHalfN * sizeof(double) + kTabEntries * 32 * sizeof(c2);
   cudaError_t e = cudaFuncSetAttribute(bsk_convert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   bsk_convert_kernel<<<kLweN * 2, 64, smem, st>>>(bsk_std, fbsk, tabs);

@@ -72,7 +72,7 @@ extern "C" void emu_bsk_to_fourier(const uint64_t* bsk, c2* fbsk) {
   for (int t = 0; t < kLweN * 2; t++) {  // (i, row): two polys each
     for (int w = 0; w < 2; w++)
       for (int lane = 0; lane < 32; lane++)
-        phaseA_load_torus(s.regs[w][lane].xr, s.regs[w][lane].xi, bsk + ((size_t)t * 2 + w) * kN, lane);
+        load_torus_poly(s.regs[w][lane].xr, s.regs[w][lane].xi, bsk + ((size_t)t * 2 + w) * kN, lane);
     forward_passes(s);
     for (int w = 0; w < 2; w++)
       for (int lane = 0; lane < 32; lane++) {
@@ -159,8 +159,8 @@ extern "C" void emu_negacyclic_mul(const int64_t* a_int, const uint64_t* b_torus
       sa.regs[0][lane].xr[r] = (double)a_int[j]; sa.regs[0][lane].xi[r] = (double)a_int[j + 1024];
       sa.regs[1][lane].xr[r] = 0; sa.regs[1][lane].xi[r] = 0;
     }
-    phaseA_load_torus(sb.regs[0][lane].xr, sb.regs[0][lane].xi, b_torus, lane);
-    phaseA_load_torus(sb.regs[1][lane].xr, sb.regs[1][lane].xi, zero.data(), lane);
+    load_torus_poly(sb.regs[0][lane].xr, sb.regs[0][lane].xi, b_torus, lane);
+    load_torus_poly(sb.regs[1][lane].xr, sb.regs[1][lane].xi, zero.data(), lane);
   }
   forward_passes(sa);
   forward_passes(sb);
@@ -177,7 +177,12 @@ extern "C" void emu_negacyclic_mul(const int64_t* a_int, const uint64_t* b_torus
   for (int w = 0; w < 2; w++)
     for (int lane = 0; lane < 32; lane++) {
       Regs& R = sa.regs[w][lane];
-      phaseC_update(R.xr, R.xi, sa.acc.data() + w * kN, lane);
+      for (int r = 0; r < 32; r++) {
+        uint32_t inc0, inc1;
+        phaseC_increments32(R.xr, R.xi, r, inc0, inc1);
+        sa.acc[w * kN + 32 * r + lane] = (uint64_t)inc0 << 32;
+        sa.acc[w * kN + 32 * r + lane + 1024] = (uint64_t)inc1 << 32;
+      }
     }
   memcpy(out, sa.acc.data(), sizeof(uint64_t) * kN);
 }
