@@ -624,22 +624,37 @@ struct Lowering {
     return combine_small(lits, is_and);
   }
 
-  // AND over a run of `len` consecutive shifts of one literal shape, by overlap doubling
-  // (AND is idempotent: run(i,L) = run(i,2^k) & run(i+L-2^k,2^k)), shared across all variants.
-  Lit run_pow2(int32_t shape, bool neg, int32_t start, int32_t len, const std::map<int32_t, int32_t>& by_base) {
+  // AND over a run of `len` consecutive shifts of one literal shape, shared across all variants.
+  // len <= 15: one sum-then-LUT node over the literals themselves; len = 15 * 2^k: overlap doubling of
+  // two half runs (AND is idempotent).  Fan-in 15 at the bottom keeps the dependent depth of a run of L
+  // positions at 1 + ceil(log2(L / 75)) levels instead of log2(L).
+  Lit run_block(int32_t shape, bool neg, int32_t start, int32_t len, const std::map<int32_t, int32_t>& by_base) {
     std::vector<int64_t> key{shape, neg ? 1 : 0, start, len};
     auto it = run_memo.find(key);
     if (it != run_memo.end()) return it->second;
     Lit r;
     if (len == 1) {
       r = Lit{by_base.at(start), neg};
+    } else if (len <= 15) {
+      std::vector<Lit> lits;
+      for (int32_t t = 0; t < len; t++) lits.push_back(Lit{by_base.at(start + t), neg});
+      r = combine_small(lits, true);
     } else {
-      Lit a = run_pow2(shape, neg, start, len / 2, by_base);
-      Lit b = run_pow2(shape, neg, start + len / 2, len / 2, by_base);
+      Lit a = run_block(shape, neg, start, len / 2, by_base);
+      Lit b = run_block(shape, neg, start + len / 2, len / 2, by_base);
       r = combine_small({a, b}, true);
     }
     run_memo.emplace(std::move(key), r);
     return r;
+  }
+  // cover [start, start+len) with at most 5 equal blocks (the last one overlapping its neighbour)
+  void cover_run(int32_t shape, bool neg, int32_t start, int32_t len, const std::map<int32_t, int32_t>& by_base, std::vector<Lit>& out) {
+    if (len <= 15) { out.push_back(run_block(shape, neg, start, len, by_base)); return; }
+    int32_t B = 15;
+    while ((len + B - 1) / B > 5) B *= 2;
+    const int32_t m = (len + B - 1) / B;
+    for (int32_t t = 0; t + 1 < m; t++) out.push_back(run_block(shape, neg, start + t * B, B, by_base));
+    out.push_back(run_block(shape, neg, start + len - B, B, by_base));
   }
 
   LitOrConst lower(int32_t root) {
@@ -731,7 +746,7 @@ struct Lowering {
     return lowered[root];
   }
 
-  // replace runs (>= 3 consecutive base positions of one literal shape) by <= 2 power-of-two run nodes
+  // replace runs (>= 3 consecutive base positions of one literal shape) by <= 5 shared run-block nodes
   std::vector<Lit> compress_runs(const std::vector<Lit>& lits) {
     std::map<std::pair<int32_t, bool>, std::vector<std::pair<int32_t, Lit>>> groups;  // (shape,neg) -> (base, lit)
     std::vector<Lit> out;
@@ -758,10 +773,7 @@ struct Lowering {
         if (!ok) {
           for (size_t t = i; t <= j; t++) out.push_back(v[t].second);
         } else {
-          int32_t p = 1;
-          while (p * 2 <= len) p *= 2;
-          out.push_back(run_pow2(g.first.first, g.first.second, start, p, by_base));
-          if (p != len) out.push_back(run_pow2(g.first.first, g.first.second, start + len - p, p, by_base));
+          cover_run(g.first.first, g.first.second, start, len, by_base, out);
         }
         i = j + 1;
       }
