@@ -122,6 +122,22 @@ def test_bootstrap_stagewise_against_oracle(client_key, server_key, gpu_key):
     assert np.abs(err).max() < PBS_ERR_MAX
 
 
+@pytest.mark.parametrize("count", [1, 2, 147, 148, 149, 296, 297, 444, 445, 592, 593, 1185])
+def test_bootstrap_batch_size_boundaries(count, fck, gpu_key):
+    # the blind rotation picks 1..4 samples per SM from the batch size; ragged last CTAs at every boundary
+    msgs = (np.arange(count) * 7 + 3) % 16
+    base = fck.encrypt_blocks(msgs[:min(count, 96)], seed=77)
+    cts = np.ascontiguousarray(np.tile(base, ((count + 95) // 96, 1))[:count])
+    msgs = np.tile(msgs[:min(count, 96)], (count + 95) // 96)[:count]
+    fs = [lambda x: (x + 5) % 16, lambda x: int(x >= 8)]
+    luts = np.stack([fb.make_lut(f) for f in fs])
+    idx = (np.arange(count) % 2).astype(np.uint32)
+    out = gpu_key.pbs(cts, luts, idx)
+    pick = sorted(set([0, count - 1, count // 2] + list(range(max(0, count - 5), count))))
+    for i in pick:
+        assert fck.decrypt_block(out[i]) == fs[int(idx[i])](int(msgs[i])) & 15, (count, i)
+
+
 def test_empty_batches(gpu_key):
     assert gpu_key.keyswitch(np.zeros((0, tfhe.BIG), dtype=np.uint64)).shape == (0, tfhe.SMALL)
     lut = tfhe.make_lut(lambda x: x)
