@@ -1,0 +1,58 @@
+// icache_probe.cu -- how much does a straight-line loop body larger than the instruction cache cost on B200?
+// One CTA of 8 warps per SM runs a loop whose body is KB kilobytes of dependent-free DFMA/IADD instructions.
+// Mode 0: all warps in lock-step.  Mode 1: odd warps start half a body later (two instruction streams per SM).
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o icache_probe icache_probe.cu && ./icache_probe
+#include <cstdio>
+#include <cuda_runtime.h>
+
+template <int N>
+__device__ __forceinline__ void body(double (&a)[8], const double m, const double c) {
+#pragma unroll
+  for (int i = 0; i < N; i++) a[i & 7] = __fma_rn(a[i & 7], m, c + (double)(i >> 3) * 1e-9);   // distinct constant -> no code folding
+}
+
+template <int N>
+__global__ void __launch_bounds__(256, 1) probe(double* sink, int iters, int mode, long long* cycles) {
+  double a[8];
+  for (int k = 0; k < 8; k++) a[k] = threadIdx.x + k;
+  const int warp = threadIdx.x >> 5;
+  const bool second_half_first = mode == 1 && (warp & 1);
+  __syncthreads();
+  const long long t0 = clock64();
+  if (second_half_first) body<N / 2>(a, 1.0000001, 1e-9);   // de-phase by half a body
+  for (int it = 0; it < iters; it++) body<N>(a, 1.0000001, 1e-9);
+  const long long t1 = clock64();
+  double s = 0;
+  for (int k = 0; k < 8; k++) s += a[k];
+  if (s == 1234.5) sink[0] = s;
+  if (threadIdx.x == 0 && blockIdx.x == 0) cycles[0] = t1 - t0;
+}
+
+template <int N>
+void run(double* sink, long long* d_cyc) {
+  const int iters = 200;
+  for (int mode = 0; mode < 2; mode++) {
+    probe<N><<<148, 256>>>(sink, iters, mode, d_cyc);
+    probe<N><<<148, 256>>>(sink, iters, mode, d_cyc);
+    cudaDeviceSynchronize();
+    long long c = 0;
+    cudaMemcpy(&c, d_cyc, sizeof c, cudaMemcpyDeviceToHost);
+    // every instruction is a DFMA (16 B): 2 warps per scheduler, 2 cycles per DFMA -> ideal 4 cycles per instruction per warp
+    printf("body %4d instr (~%3d KB)  mode %d  cycles/iter %9.0f  cycles/instr %.3f\n", N, N * 16 / 1024, mode, (double)c / iters, (double)c / iters / N);
+  }
+}
+
+int main() {
+  double* sink; long long* d_cyc;
+  cudaMalloc(&sink, 8); cudaMalloc(&d_cyc, 8);
+  run<512>(sink, d_cyc);
+  run<1024>(sink, d_cyc);
+  run<2048>(sink, d_cyc);
+  run<3072>(sink, d_cyc);
+  run<4096>(sink, d_cyc);
+  run<6144>(sink, d_cyc);
+  run<8192>(sink, d_cyc);
+  cudaError_t e = cudaGetLastError();
+  printf("%s\n", cudaGetErrorString(e));
+  return 0;
+}
