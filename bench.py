@@ -332,8 +332,16 @@ def main():
         c64 = "".join(rng.choice(list("abcx"), size=64))
         matches = []
         c256 = "".join(np.random.default_rng(6).choice(list("abx"), size=256))   # no 'c': every variant must be evaluated
-        cases = [(c64, "/a+b?c/"), (c64, "/ab{2,4}c/"), (c64, r"/[a-d][^x-z]\./"), (c256, "/a+b?c/")]
-        for content, pattern in cases:
+        # (content, pattern, reference_shaped): the default plan absorbs OR operands implied by another operand
+        # (decrypt-identical, O(n) instead of O(n^2) PBS for /a+.../); FB_PLAN_NO_ABSORB=1 evaluates every variant
+        # the reference enumerates -- the large sharded PBS batch BASELINE.json's config 5 describes.
+        cases = [(c64, "/a+b?c/", False), (c64, "/ab{2,4}c/", False), (c64, r"/[a-d][^x-z]\./", False), (c256, "/a+b?c/", False),
+                 (c64, "/a+b?c/", True), (c256, "/a+b?c/", True)]
+        for content, pattern, ref_shaped in cases:
+            if ref_shaped:
+                os.environ["FB_PLAN_NO_ABSORB"] = "1"
+            else:
+                os.environ.pop("FB_PLAN_NO_ABSORB", None)
             ct = fb.encrypt_str(ck, content, seed=9)
             barrier()
             tc = time.perf_counter()
@@ -354,12 +362,16 @@ def main():
                 res = ck.decrypt(part)
                 exp = rp.has_match(content, pattern)
                 assert res == exp, (pattern, res, exp)
-                matches.append({"pattern": pattern, "n_chars": len(content), "ms": wall, "ms_cold_rank0": cold, "gpu_ms_rank0": st["gpu_ms"], "pbs_rank0": st["pbs"],
+                matches.append({"pattern": pattern, "n_chars": len(content), "plan": "reference-shaped" if ref_shaped else "absorbed",
+                                "ms": wall, "ms_cold_rank0": cold, "gpu_ms_rank0": st["gpu_ms"], "pbs_rank0": st["pbs"],
                                 "levels": st["levels"], "ref_ct_ops_rank0": st["ct_ops"], "result": res})
+        os.environ.pop("FB_PLAN_NO_ABSORB", None)
         if rank == 0:
             line["match"] = matches
             line["ms_per_match_64"] = matches[0]["ms"]
-            line["ms_per_match_256"] = matches[-1]["ms"]
+            line["ms_per_match_256"] = matches[3]["ms"]
+            line["ms_per_match_64_reference_shaped"] = matches[4]["ms"]
+            line["ms_per_match_256_reference_shaped"] = matches[5]["ms"]
 
     sk.close()
     if rank == 0:

@@ -5,6 +5,7 @@
 // Replaces has_match (engine.rs:8-42) + Execution (execution.rs:37-223) of the reference.
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -169,7 +170,8 @@ extern "C" int fb_plan_eval_plain(const char* pattern, const uint8_t* content, s
 extern "C" int fb_has_match_shard(fb_ctx* ctx, const uint64_t* h_content, size_t n_chars, const char* pattern, int rank,
                                   int world, uint64_t* h_out, fb_match_stats* stats) {
   if (!ctx || !pattern || !h_out || (!h_content && n_chars)) return fb_fail(ctx, FB_ERR_ARG, "null argument");
-  const std::string key = std::string(pattern) + '\n' + std::to_string(n_chars) + '/' + std::to_string(rank) + '/' + std::to_string(world);
+  const std::string key = std::string(pattern) + '\n' + std::to_string(n_chars) + '/' + std::to_string(rank) + '/' + std::to_string(world) +
+                          (std::getenv("FB_PLAN_NO_ABSORB") ? "/ref-shaped" : "/absorbed");
   std::shared_ptr<const Plan> plan;
   for (size_t i = 0; i < ctx->plan_cache.size(); i++)
     if (ctx->plan_cache[i].first == key) {

@@ -4,6 +4,7 @@
 // against deep-cloned provenance trees; here variants are integer thunks and provenance is hash-consed.
 #include "regex_host.h"
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 
@@ -534,6 +535,9 @@ struct Lowering {
   std::vector<LitOrConst> lowered;                          // value id -> literal (kind -1: not lowered yet)
   std::vector<uint32_t> seen_stamp;                         // flattening scratch: value id -> generation
   uint32_t seen_gen = 0;
+  bool absorb = true;                                       // drop OR operands implied by another operand (x | (x & y) = x)
+  std::unordered_map<int32_t, std::vector<Lit>> and_sets;   // PBS node of a lowered AND -> its full literal set
+  uint64_t absorbed = 0;
   std::map<std::vector<int64_t>, int32_t> shape_intern;    // shift-invariant structure -> shape id
   std::unordered_map<int32_t, std::pair<int32_t, int32_t>> node_shape;  // PBS node -> (shape, base position)
   std::map<int32_t, std::map<int32_t, int32_t>> shape_nodes;           // shape -> base position -> PBS node
@@ -657,6 +661,58 @@ struct Lowering {
     out.push_back(run_block(shape, neg, start + len - B, B, by_base));
   }
 
+  // Absorption over the operands of an OR: an operand that is the AND of a superset of another operand's
+  // literals is implied by it (x | (x & y) = x) and is dropped; the boolean function, hence the decrypted
+  // result, is unchanged.  This is what turns the reference's O(n^2) variants of an unanchored /a+.../ into
+  // O(n) bootstraps: the variant that starts at i with run length L contains the literals of the variant
+  // that starts at i+L-1 with run length 1.  Sets are sorted literal lists; candidates are visited by
+  // increasing size and looked up through the kept sets indexed by their rarest literal.
+  static uint64_t lit_key(const Lit& l) { return ((uint64_t)(uint32_t)l.node << 1) | (l.neg ? 1u : 0u); }
+  void absorb_or_operands(std::vector<Lit>& ops) {
+    struct Item { std::vector<uint64_t> set; Lit lit; };
+    std::vector<Item> items;
+    items.reserve(ops.size());
+    for (auto& l : ops) {
+      Item it{{}, l};
+      auto f = l.neg ? and_sets.end() : and_sets.find(l.node);
+      if (f != and_sets.end()) for (auto& x : f->second) it.set.push_back(lit_key(x));
+      else it.set.push_back(lit_key(l));
+      std::sort(it.set.begin(), it.set.end());
+      items.push_back(std::move(it));
+    }
+    std::unordered_map<uint64_t, uint32_t> freq;                  // literal -> number of operand sets holding it
+    for (auto& it : items)
+      for (uint64_t x : it.set) freq[x]++;
+    std::vector<size_t> order(items.size());
+    for (size_t i = 0; i < order.size(); i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return items[a].set.size() < items[b].set.size(); });
+    std::unordered_map<uint64_t, std::vector<size_t>> by_rare;    // rarest literal of a kept set -> kept items
+    std::vector<Lit> kept;
+    uint64_t budget = 2000000000ull;                               // literal comparisons; beyond it the rest is kept as is
+    for (size_t oi : order) {
+      const auto& B = items[oi].set;
+      bool implied = false;
+      for (size_t xi2 = 0; xi2 < B.size() && !implied && budget > 0; xi2++) {
+        auto f = by_rare.find(B[xi2]);
+        if (f == by_rare.end()) continue;
+        for (size_t ai : f->second) {
+          const auto& A = items[ai].set;
+          if (A.size() > B.size()) continue;
+          budget -= std::min<uint64_t>(budget, A.size() + B.size());
+          if (std::includes(B.begin(), B.end(), A.begin(), A.end())) { implied = true; break; }
+        }
+      }
+      if (implied) { absorbed++; continue; }
+      uint64_t rare = B[0];
+      for (uint64_t x : B)
+        if (freq[x] < freq[rare]) rare = x;
+      by_rare[rare].push_back(oi);
+      kept.push_back(items[oi].lit);
+    }
+    std::sort(kept.begin(), kept.end(), [](const Lit& x, const Lit& y) { return x.node < y.node || (x.node == y.node && x.neg < y.neg); });
+    ops.swap(kept);
+  }
+
   LitOrConst lower(int32_t root) {
     // iterative post-order over the value DAG (the sequential OR fold is tens of thousands deep)
     std::vector<int32_t> stack{root};
@@ -736,10 +792,12 @@ struct Lowering {
       }
       if (decided) { stack.pop_back(); continue; }
       if (lits.empty()) { lowered[v] = LitOrConst{is_and ? 1 : 0, {0, false}}; stack.pop_back(); continue; }
+      if (!is_and && absorb && lits.size() > 1) absorb_or_operands(lits);
       const std::vector<Lit> full = lits;
       if (is_and && lits.size() > 2) lits = compress_runs(lits);
       const Lit r = combine(lits, is_and);
       lowered[v] = LitOrConst{2, r};
+      if (is_and && absorb && !r.neg && full.size() > 1) and_sets.emplace(r.node, full);
       if (full.size() > 1 && !r.neg) register_set_shape(r.node, full, is_and);
       stack.pop_back();
     }
@@ -915,6 +973,7 @@ int build_plan(const std::string& pattern, size_t n_chars, int rank, int world, 
       }
     }
     Lowering L(ex, n_chars);
+    L.absorb = std::getenv("FB_PLAN_NO_ABSORB") == nullptr;   // reference-shaped plan (every variant evaluated) when set
     LitOrConst out = L.lower(res.val);
     plan = Plan();
     emit_plan(L, out, n_chars, plan);
