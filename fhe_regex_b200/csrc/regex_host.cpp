@@ -355,16 +355,34 @@ struct TripleHash {
     return (size_t)(h ^ (h >> 31));
   }
 };
-struct Interner {
-  std::unordered_map<Triple, int32_t, TripleHash> map;
+struct Interner {  // hash-consing table: open addressing over a power-of-two slot array (ids index `items`)
+  std::vector<int32_t> slots;
   std::vector<Triple> items;
+  size_t mask = 0;
+  Interner() { slots.assign(1 << 12, -1); mask = slots.size() - 1; }
+  void grow() {
+    std::vector<int32_t> bigger(slots.size() * 2, -1);
+    const size_t m = bigger.size() - 1;
+    TripleHash h;
+    for (int32_t id = 0; id < (int32_t)items.size(); id++) {
+      size_t p = h(items[id]) & m;
+      while (bigger[p] >= 0) p = (p + 1) & m;
+      bigger[p] = id;
+    }
+    slots.swap(bigger);
+    mask = m;
+  }
   int32_t get(int32_t t, int32_t a, int32_t b) {
-    Triple k{t, a, b};
-    auto it = map.find(k);
-    if (it != map.end()) return it->second;
-    int32_t id = (int32_t)items.size();
+    const Triple k{t, a, b};
+    size_t p = TripleHash()(k) & mask;
+    while (slots[p] >= 0) {
+      if (items[slots[p]] == k) return slots[p];
+      p = (p + 1) & mask;
+    }
+    const int32_t id = (int32_t)items.size();
     items.push_back(k);
-    map.emplace(k, id);
+    slots[p] = id;
+    if (items.size() * 2 > slots.size()) grow();
     return id;
   }
 };
