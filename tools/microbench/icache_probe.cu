@@ -31,15 +31,17 @@ __global__ void __launch_bounds__(256, 1) probe(double* sink, int iters, int mod
 template <int N>
 void run(double* sink, long long* d_cyc) {
   const int iters = 200;
-  for (int mode = 0; mode < 2; mode++) {
-    probe<N><<<148, 256>>>(sink, iters, mode, d_cyc);
-    probe<N><<<148, 256>>>(sink, iters, mode, d_cyc);
-    cudaDeviceSynchronize();
-    long long c = 0;
-    cudaMemcpy(&c, d_cyc, sizeof c, cudaMemcpyDeviceToHost);
-    // every instruction is a DFMA (16 B): 2 warps per scheduler, 2 cycles per DFMA -> ideal 4 cycles per instruction per warp
-    printf("body %4d instr (~%3d KB)  mode %d  cycles/iter %9.0f  cycles/instr %.3f\n", N, N * 16 / 1024, mode, (double)c / iters, (double)c / iters / N);
-  }
+  const int grids[3] = {37, 74, 148};   // 148 CTAs: both SMs of every TPC are busy
+  for (int g = 0; g < 3; g++)
+    for (int mode = 0; mode < 2; mode++) {
+      probe<N><<<grids[g], 256>>>(sink, iters, mode, d_cyc);
+      probe<N><<<grids[g], 256>>>(sink, iters, mode, d_cyc);
+      cudaDeviceSynchronize();
+      long long c = 0;
+      cudaMemcpy(&c, d_cyc, sizeof c, cudaMemcpyDeviceToHost);
+      // every instruction is a DFMA (16 B): 2 warps per scheduler, 2 cycles per DFMA -> ideal 4 cycles per instruction per warp
+      printf("body %4d instr (~%3d KB)  CTAs %3d  mode %d  cycles/instr %.3f\n", N, N * 16 / 1024, grids[g], mode, (double)c / iters / N);
+    }
 }
 
 int main() {
