@@ -23,7 +23,7 @@ __device__ __forceinline__ void bar_sync(int id, int nthreads) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(64, 1)
 bsk_convert_kernel(const uint64_t* __restrict__ bsk_std, c2* __restrict__ fbsk, const c2* __restrict__ tabs_g) {
-  extern __shared__ __align__(16) unsigned char smem[];
+  extern __shared__ __align__(128) unsigned char smem[];
   double* plane = reinterpret_cast<double*>(smem);            // [2][1024]
   c2* tab_f = reinterpret_cast<c2*>(plane + 2 * kHalfN);       // [12][32]
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
