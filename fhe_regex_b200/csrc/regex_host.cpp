@@ -556,6 +556,7 @@ struct Lowering {
   bool absorb = true;                                       // drop OR operands implied by another operand (x | (x & y) = x)
   std::unordered_map<int32_t, std::vector<Lit>> and_sets;   // PBS node of a lowered AND -> its full literal set
   uint64_t absorbed = 0;
+  std::vector<std::pair<int32_t, int32_t>> eq_parts;         // eq node -> its two nibble-test nodes (eq = their AND), or (-1,-1)
   std::map<std::vector<int64_t>, int32_t> shape_intern;    // shift-invariant structure -> shape id
   std::unordered_map<int32_t, std::pair<int32_t, int32_t>> node_shape;  // PBS node -> (shape, base position)
   std::map<int32_t, std::map<int32_t, int32_t>> shape_nodes;           // shape -> base position -> PBS node
@@ -744,6 +745,10 @@ struct Lowering {
         Lit r = combine_small({e0, e1}, true);
         lowered[v] = LitOrConst{2, r};
         register_shape(r.node, {V_EQ, t.b}, t.a);
+        register_shape(e0.node, {-10, t.b & 15}, t.a);          // nibble tests are shiftable shapes too
+        register_shape(e1.node, {-11, (t.b >> 4) & 15}, t.a);
+        if ((size_t)r.node >= eq_parts.size()) eq_parts.resize(std::max<size_t>((size_t)r.node + 1, eq_parts.size() * 2), {-1, -1});
+        eq_parts[r.node] = {e0.node, e1.node};
         stack.pop_back();
         continue;
       }
@@ -809,10 +814,28 @@ struct Lowering {
         else lits.resize(o);
       }
       if (decided) { stack.pop_back(); continue; }
+      if (is_and && lits.size() > 1) {
+        // a plain eq under an AND is itself the AND of two nibble tests: use those directly, which takes the
+        // eq-combine level off the dependent path (the eq node stays for consumers that need it whole)
+        std::vector<Lit> flat;
+        bool changed = false;
+        for (auto& l : lits) {
+          if (l.neg || (size_t)l.node >= eq_parts.size() || eq_parts[l.node].first < 0) { flat.push_back(l); continue; }
+          flat.push_back(Lit{eq_parts[l.node].first, false});
+          flat.push_back(Lit{eq_parts[l.node].second, false});
+          changed = true;
+        }
+        if (changed) {
+          std::sort(flat.begin(), flat.end(), [](const Lit& x, const Lit& y) { return x.node < y.node || (x.node == y.node && x.neg < y.neg); });
+          flat.erase(std::unique(flat.begin(), flat.end(), [](const Lit& x, const Lit& y) { return x.node == y.node && x.neg == y.neg; }), flat.end());
+          lits.swap(flat);
+        }
+      }
       if (lits.empty()) { lowered[v] = LitOrConst{is_and ? 1 : 0, {0, false}}; stack.pop_back(); continue; }
       if (!is_and && absorb && lits.size() > 1) absorb_or_operands(lits);
       const std::vector<Lit> full = lits;
-      if (is_and && lits.size() > 2) lits = compress_runs(lits);
+      // one sum-then-LUT node takes up to 15 literals: shared run blocks are only worth a level beyond that
+      if (is_and && lits.size() > 15) lits = compress_runs(lits, 3);
       const Lit r = combine(lits, is_and);
       lowered[v] = LitOrConst{2, r};
       if (is_and && absorb && !r.neg && full.size() > 1) and_sets.emplace(r.node, full);
@@ -823,7 +846,7 @@ struct Lowering {
   }
 
   // replace runs (>= 3 consecutive base positions of one literal shape) by <= 5 shared run-block nodes
-  std::vector<Lit> compress_runs(const std::vector<Lit>& lits) {
+  std::vector<Lit> compress_runs(const std::vector<Lit>& lits, int32_t min_run) {
     std::map<std::pair<int32_t, bool>, std::vector<std::pair<int32_t, Lit>>> groups;  // (shape,neg) -> (base, lit)
     std::vector<Lit> out;
     for (auto& l : lits) {
@@ -840,7 +863,7 @@ struct Lowering {
         size_t j = i;
         while (j + 1 < v.size() && v[j + 1].first == v[j].first + 1) j++;
         const int32_t len = (int32_t)(j - i + 1), start = v[i].first;
-        bool ok = len >= 3;
+        bool ok = len >= min_run;   // short runs are cheaper as plain literals (a block node costs a level)
         // every position of the run must map to the very node we hold
         for (size_t t = i; ok && t <= j; t++) {
           auto gi = by_base.find(v[t].first);
