@@ -423,7 +423,9 @@ cudaError_t launch_blind_rotate(const c2* fbsk, const uint64_t* small, const uin
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
   }
-  if (count <= sms) return launch_br_s<1>(fbsk, small, luts, lut_idx, out, out_rows, tabs, count, st);
+  // measured (tools/wave_times.py): one sample per SM on all 148 SMs takes 6.6 ms, two per SM on 74-148 SMs 5.9 ms,
+  // one per SM on <= 74 SMs 4.9-5.7 ms -- a lone sample per SM is only worth it while half the SMs stay idle
+  if (2 * count <= sms) return launch_br_s<1>(fbsk, small, luts, lut_idx, out, out_rows, tabs, count, st);
   if (count <= 2 * sms) return launch_br_s<2>(fbsk, small, luts, lut_idx, out, out_rows, tabs, count, st);
   if (count <= 3 * sms) return launch_br_s<3>(fbsk, small, luts, lut_idx, out, out_rows, tabs, count, st);
   return launch_br_s<4>(fbsk, small, luts, lut_idx, out, out_rows, tabs, count, st);

@@ -122,7 +122,7 @@ def test_bootstrap_stagewise_against_oracle(client_key, server_key, gpu_key):
     assert np.abs(err).max() < PBS_ERR_MAX
 
 
-@pytest.mark.parametrize("count", [1, 2, 147, 148, 149, 296, 297, 444, 445, 592, 593, 1185])
+@pytest.mark.parametrize("count", [1, 2, 74, 75, 148, 149, 296, 297, 444, 445, 592, 593, 1185])
 def test_bootstrap_batch_size_boundaries(count, fck, gpu_key):
     # the blind rotation picks 1..4 samples per SM from the batch size; ragged last CTAs at every boundary
     msgs = (np.arange(count) * 7 + 3) % 16
@@ -179,6 +179,22 @@ def test_has_match_64_char_configs(fck, gpu_key):
                              ("x" * 64, "/a+b?c/"), (c64, r"/^[a-d][^x-z]\.$/")]:
         res = fb.has_match(gpu_key, fb.encrypt_str(fck, content, seed=9), pattern)
         assert fck.decrypt(res) == rp.has_match(content, pattern), (content, pattern)
+
+
+def test_has_match_256_char_config5_both_plans(fck, gpu_key, monkeypatch):
+    # BASELINE config 5 at full size: 65 025 variants; the reference-shaped plan evaluates all of them (~76k PBS),
+    # the default plan absorbs implied variants (~1.6k PBS); both must decrypt to the reference's result
+    rng = np.random.default_rng(12)
+    miss = "".join(rng.choice(list("abx"), size=256))                    # no 'c': no match
+    hit = miss[:200] + "aabc" + miss[204:]
+    for content in (miss, hit):
+        ct = fb.encrypt_str(fck, content, seed=13)
+        exp = rp.has_match(content, "/a+b?c/")
+        res, st = fb.has_match(gpu_key, ct, "/a+b?c/", return_stats=True)
+        assert fck.decrypt(res) == exp and st["pbs"] < 3000 and st["variants"] == 65025
+    monkeypatch.setenv("FB_PLAN_NO_ABSORB", "1")
+    res, st = fb.has_match(gpu_key, fb.encrypt_str(fck, hit, seed=13), "/a+b?c/", return_stats=True)
+    assert fck.decrypt(res) == 1 and st["pbs"] > 60000 and (st["ct_ops"], st["cache_hits"]) == (195583, 11118596)
 
 
 def test_sharded_match_and_or_fold(fck, gpu_key):
