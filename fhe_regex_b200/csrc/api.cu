@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include "context.h"
@@ -55,14 +56,19 @@ extern "C" int fb_ctx_create(fb_ctx** out, int device) {
     return FB_ERR_CUDA;
   }
   // twiddle tables
-  std::vector<c2> tabs(2 * fb::kTabEntries * 32);
+  // (the table of the latency kernel rides behind the two 12x32 tables of the throughput kernel)
+  const size_t n_tabs = 2 * fb::kTabEntries * 32;
+  std::vector<c2> tabs(n_tabs + fb::br_wide_table_bytes() / sizeof(c2));
   fb::make_twiddle_tables(tabs.data(), tabs.data() + fb::kTabEntries * 32);
+  fb::br_wide_make_table(tabs.data() + n_tabs);
+  if (const char* w = std::getenv("FB_WIDE_MAX")) ctx->wide_max = std::atoi(w);
   if (cudaMalloc(&ctx->d_tabs, tabs.size() * sizeof(c2)) != cudaSuccess ||
       cudaMemcpy(ctx->d_tabs, tabs.data(), tabs.size() * sizeof(c2), cudaMemcpyHostToDevice) != cudaSuccess) {
     delete ctx;
     g_create_err = "twiddle table upload failed";
     return FB_ERR_CUDA;
   }
+  ctx->d_wtab = ctx->d_tabs + n_tabs;
   *out = ctx;
   return FB_OK;
 }
@@ -197,7 +203,11 @@ int fb_run_blind_rotate(fb_ctx* ctx, const uint64_t* d_small, const uint64_t* d_
                         uint64_t* d_out, const int32_t* d_out_rows, int count) {
   fb_event_pair ev;
   bool t = timing_begin(ctx, 1, ev);
-  cudaError_t e = fb::launch_blind_rotate(ctx->d_fbsk, d_small, d_luts, d_lut_idx, d_out, d_out_rows, ctx->d_tabs, count, ctx->stream);
+  // a level narrower than two waves of SMs is latency: one PBS per CTA (br_wide.cu); otherwise throughput
+  // (kernels.cu, up to 4 PBS per CTA)
+  cudaError_t e = (count <= ctx->wide_max)
+                      ? fb::launch_blind_rotate_wide(ctx->d_fbsk, d_small, d_luts, d_lut_idx, d_out, d_out_rows, ctx->d_wtab, count, ctx->stream)
+                      : fb::launch_blind_rotate(ctx->d_fbsk, d_small, d_luts, d_lut_idx, d_out, d_out_rows, ctx->d_tabs, count, ctx->stream);
   timing_end(ctx, t, ev);
   if (e != cudaSuccess) return fb_cuda_fail(ctx, e, "blind_rotate_kernel launch");
   ctx->ks.br_launches++;
@@ -232,6 +242,12 @@ static int resolve_pending(fb_ctx* ctx) {
   }
   ctx->pending.clear();
   return FB_OK;
+}
+extern "C" int fb_set_latency_threshold(fb_ctx* ctx, int max_count) {
+  if (!ctx || max_count < 0) return FB_ERR_ARG;
+  const int prev = ctx->wide_max;
+  ctx->wide_max = max_count;
+  return prev;
 }
 extern "C" int fb_kernel_stats_reset(fb_ctx* ctx) {
   if (!ctx) return FB_ERR_ARG;

@@ -29,6 +29,8 @@ struct fb_ctx {
   uint8_t* d_kb = nullptr;     // byte planes of the KSK for the tensor-core keyswitch
   fb::c2* d_fbsk = nullptr;
   fb::c2* d_tabs = nullptr;
+  fb::c2* d_wtab = nullptr;    // table of the latency blind rotation (inside the d_tabs allocation)
+  int wide_max = 296;          // batches up to this many PBS take the latency kernel (env FB_WIDE_MAX; 0 = never)
   bool have_key = false;
   // scratch for the batch entry points
   fb_devbuf in, small, out, luts, lut_idx, digits;

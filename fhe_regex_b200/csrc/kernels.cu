@@ -11,6 +11,7 @@
 #include <stdint.h>
 #include "br_core.cuh"
 #include "kernels.h"
+#include "ptx_sync.cuh"
 
 namespace fb {
 
@@ -69,35 +70,6 @@ bsk_convert_kernel(const uint64_t* __restrict__ bsk_std, c2* __restrict__ fbsk, 
 //                + 12 KiB twiddles + S * 1.5 KiB mod-switched mask + 768 B step flags + mbarrier.
 // ------------------------------------------------------------------------------------------------
 constexpr int kGgswBytes = 4 * kHalfN * (int)sizeof(c2);  // 65536
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// whole-warp wait: the exit condition is a vote, so the warp provably leaves the loop converged (a per-thread
-// exit makes ptxas wrap every later shuffle in WARPSYNC.COLLECTIVE / ENDCOLLECTIVE with register moves)
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-  } while (!__all_sync(0xffffffffu, done));
-}
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
-               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
 
 // ---- tensor memory (TMEM) as thread-private storage of the accumulators ----------------------------
 // TMEM is 128 lanes x 512 32-bit columns per SM; warp w of a CTA may touch lanes 32*(w%4) .. +31 only, and

@@ -9,6 +9,11 @@ size_t br_smem_bytes(int S);
 cudaError_t launch_bsk_convert(const uint64_t* bsk_std, c2* fbsk, const c2* tabs, cudaStream_t st);
 cudaError_t launch_blind_rotate(const c2* fbsk, const uint64_t* small, const uint64_t* luts, const uint32_t* lut_idx,
                                 uint64_t* out, const int32_t* out_rows, const c2* tabs, int count, cudaStream_t st);
+// latency variant: one PBS per CTA (br_wide.cu)
+size_t br_wide_table_bytes();
+void br_wide_make_table(c2* host_tab);
+cudaError_t launch_blind_rotate_wide(const c2* fbsk, const uint64_t* small, const uint64_t* luts, const uint32_t* lut_idx,
+                                     uint64_t* out, const int32_t* out_rows, const c2* wtab, int count, cudaStream_t st);
 cudaError_t launch_lincomb(uint64_t* arena, const int32_t* out_rows, const int32_t* term_off, const int32_t* term_rows,
                            const int64_t* term_coef, const uint64_t* body_const, int n_out, cudaStream_t st);
 // keyswitch as an int8 tensor-core contraction (ks_kernels.cu)

@@ -135,6 +135,10 @@ int fb_kernel_timing_enable(fb_ctx* ctx, int on);
 /* FP64 FMA-pipe throughput of the device in TFLOP/s (dependent-chain DFMA probe, best of reps): the
  * roofline denominator of the blind rotation */
 int fb_measure_fp64_peak(fb_ctx* ctx, int reps, double* tflops);
+/* Batches of up to max_count PBS run the latency variant of the blind rotation (one PBS per CTA, br_wide.cu);
+ * larger ones the throughput variant (up to 4 PBS per CTA).  Default 296 (two waves of 148 SMs), 0 = never.
+ * Returns the previous value (or a negative error code).  Both variants compute the same function. */
+int fb_set_latency_threshold(fb_ctx* ctx, int max_count);
 /* PBS batch sizes that fill the GPU evenly are multiples of this (SM count x samples per CTA) */
 int fb_pbs_batch_quantum(fb_ctx* ctx);
 

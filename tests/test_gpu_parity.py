@@ -73,7 +73,15 @@ def test_fourier_key_matches_emulation(server_key, gpu_key):
     assert np.abs(got - exp).max() < 1e-11 * scale
 
 
-def test_bootstrap_trivial_inputs_bit_exact(server_key, gpu_key):
+@pytest.fixture(params=["latency", "throughput"])
+def br_variant(request, gpu_key):
+    """small batches through both blind rotations: one PBS per CTA (br_wide.cu) / up to 4 per CTA (kernels.cu)"""
+    prev = gpu_key.set_latency_threshold(0 if request.param == "throughput" else 1 << 30)
+    yield request.param
+    gpu_key.set_latency_threshold(prev)
+
+
+def test_bootstrap_trivial_inputs_bit_exact(server_key, gpu_key, br_variant):
     # trivial ciphertexts (what the reference's tests use, engine.rs:282-286): every CMUX is skipped,
     # the result is pure integer work -> bit-exact against the oracle
     fs = [lambda x: x, lambda x: (3 * x) % 16, lambda x: int(x >= 1)]
@@ -107,7 +115,7 @@ def test_bootstrap_decrypt_and_noise(client_key, server_key, gpu_key):
     assert tfhe.torus_err(ph_ref, exp_msg[sub] << np.uint64(59)).std() < PBS_ERR_STD_MAX
 
 
-def test_bootstrap_stagewise_against_oracle(client_key, server_key, gpu_key):
+def test_bootstrap_stagewise_against_oracle(client_key, server_key, gpu_key, br_variant):
     # same keyswitched inputs into both blind rotations
     msgs = np.arange(32) % 16
     cts = tfhe.encrypt_batch(client_key, msgs, seed=41)
@@ -123,8 +131,11 @@ def test_bootstrap_stagewise_against_oracle(client_key, server_key, gpu_key):
 
 
 @pytest.mark.parametrize("count", [1, 2, 74, 75, 148, 149, 296, 297, 444, 445, 592, 593, 1185])
-def test_bootstrap_batch_size_boundaries(count, fck, gpu_key):
-    # the blind rotation picks 1..4 samples per SM from the batch size; ragged last CTAs at every boundary
+def test_bootstrap_batch_size_boundaries(count, fck, gpu_key, br_variant):
+    # the throughput blind rotation picks 1..4 samples per SM from the batch size (ragged last CTAs at every
+    # boundary); the latency one runs in waves of one CTA per PBS
+    if br_variant == "latency" and count > 445:
+        pytest.skip("latency variant is never chosen for wide batches")
     msgs = (np.arange(count) * 7 + 3) % 16
     base = fck.encrypt_blocks(msgs[:min(count, 96)], seed=77)
     cts = np.ascontiguousarray(np.tile(base, ((count + 95) // 96, 1))[:count])
@@ -136,6 +147,33 @@ def test_bootstrap_batch_size_boundaries(count, fck, gpu_key):
     pick = sorted(set([0, count - 1, count // 2] + list(range(max(0, count - 5), count))))
     for i in pick:
         assert fck.decrypt_block(out[i]) == fs[int(idx[i])](int(msgs[i])) & 15, (count, i)
+
+
+def test_latency_and_throughput_variants_agree(client_key, gpu_key):
+    """same keyswitched inputs through both blind rotations: same decryptions, outputs within FFT rounding"""
+    n = 150
+    msgs = np.arange(n) % 16
+    cts = tfhe.encrypt_batch(client_key, msgs, seed=53)
+    fs = [lambda x: (x * 3 + 2) % 16, lambda x: int(x == 2)]
+    luts = np.stack([tfhe.make_lut(f) for f in fs])
+    idx = (np.arange(n) % 2).astype(np.uint32)
+    outs = {}
+    for name, thr in (("latency", 1 << 30), ("throughput", 0)):
+        prev = gpu_key.set_latency_threshold(thr)
+        try:
+            outs[name] = gpu_key.pbs(cts, luts, idx)
+        finally:
+            gpu_key.set_latency_threshold(prev)
+    exp_msg = np.array([fs[i](int(m)) & 15 for m, i in zip(msgs, idx)], dtype=np.uint64)
+    for name, got in outs.items():
+        ph = tfhe.phase_batch(client_key.big, got)
+        dec = ((ph + np.uint64(1 << 58)) >> np.uint64(59)) & np.uint64(15)
+        assert (dec == exp_msg).all(), name
+        err = tfhe.torus_err(ph, exp_msg << np.uint64(59))
+        assert np.abs(err).max() < PBS_ERR_MAX and err.std() < PBS_ERR_STD_MAX, name
+    # word by word the two outputs differ by f64 rounding only (both accumulate on 32 torus bits)
+    d = (outs["latency"] - outs["throughput"]).view(np.int64).astype(np.float64) / 2.0 ** 64
+    assert np.abs(d).max() < 2.0 ** -20, np.abs(d).max()
 
 
 def test_empty_batches(gpu_key):
