@@ -24,12 +24,13 @@ constexpr int kBufBytes = 2 * kHalfN * (int)sizeof(c2);    // 32768
 constexpr size_t kOffBufA = 2 * (size_t)kStageBytes;
 constexpr size_t kOffBufB = kOffBufA + kBufBytes;
 constexpr size_t kOffAcc = kOffBufB + kBufBytes;
-constexpr size_t kOffTab3 = kOffAcc + 2 * kN * sizeof(uint32_t);
-constexpr size_t kOffAt = kOffTab3 + 32 * sizeof(c2);
+constexpr size_t kOffAt = kOffAcc + 2 * kN * sizeof(uint32_t);
 constexpr size_t kOffSteps = kOffAt + 768 * sizeof(uint16_t);
 constexpr size_t kOffBars = kOffSteps + 768 * sizeof(uint16_t);
 constexpr size_t kWideSmem = kOffBars + 2 * sizeof(uint64_t) + 16;
 }  // namespace
+
+__device__ __forceinline__ void half_sync(int P) { asm volatile("bar.sync %0, 128;" ::"r"(1 + P) : "memory"); }
 
 __global__ void __launch_bounds__(wide::kThreads, 1)
 blind_rotate_wide_kernel(const c2* __restrict__ fbsk, const uint64_t* __restrict__ small, const uint64_t* __restrict__ luts,
@@ -39,7 +40,6 @@ blind_rotate_wide_kernel(const c2* __restrict__ fbsk, const uint64_t* __restrict
   c2* bufA = reinterpret_cast<c2*>(smem + kOffBufA);
   c2* bufB = reinterpret_cast<c2*>(smem + kOffBufB);
   uint32_t* acc = reinterpret_cast<uint32_t*>(smem + kOffAcc);
-  c2* tab3 = reinterpret_cast<c2*>(smem + kOffTab3);            // [fwd/inv][p3][8]
   uint16_t* at = reinterpret_cast<uint16_t*>(smem + kOffAt);      // mod-switched ciphertext, bit 15: step needed
   uint16_t* steps = reinterpret_cast<uint16_t*>(smem + kOffSteps);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kOffBars);
@@ -51,7 +51,6 @@ blind_rotate_wide_kernel(const c2* __restrict__ fbsk, const uint64_t* __restrict
 
   wide::Tw tw;
   wide::load_tw(tw, wtab, t);
-  if (tid < 32) tab3[tid] = wtab[wide::kTwRegs * 128 + tid];
   for (int i = tid; i < 768; i += wide::kThreads) {
     uint32_t a = 0;
     if (i < kSmall) {
@@ -97,8 +96,6 @@ blind_rotate_wide_kernel(const c2* __restrict__ fbsk, const uint64_t* __restrict
   uint32_t* accp = acc + P * kN;
   c2* bufA_p = bufA + P * kHalfN;
   c2* bufB_p = bufB + P * kHalfN;
-  const c2* tab3f = tab3;
-  const c2* tab3i = tab3 + 16;
 
 #pragma unroll 1
   for (int n = 0; n < n_steps; n++) {
@@ -106,22 +103,25 @@ blind_rotate_wide_kernel(const c2* __restrict__ fbsk, const uint64_t* __restrict
     const uint32_t a = (uint32_t)at[i] & 4095u;
     // the other stage was last read by the MAC of step n-1, four barriers ago
     if (tid == 0 && n + 1 < n_steps) issue_ggsw(steps[n + 1], (n + 1) & 1);
+    // The two polynomials only meet in the Fourier MAC: everywhere else a half (128 threads) synchronises on its
+    // own named barrier, so one half's transform arithmetic overlaps the other half's shared-memory traffic.
     wide::fwd_stage1(accp, a, t, tw, bufA_p);
-    __syncthreads();
+    half_sync(P);
     wide::fwd_stage2(bufA_p, bufB_p, t, tw);
-    __syncthreads();
-    wide::fwd_stage3(bufB_p, bufA_p, t, tab3f);
-    __syncthreads();
+    half_sync(P);
+    wide::fwd_stage3(bufB_p, bufA_p, t);
+    __syncthreads();                              // both spectra complete
     mbar_wait(full_bar + (n & 1), (uint32_t)(n >> 1) & 1u);
     wide::mac_inv_stage1(bufA, bufA + kHalfN, reinterpret_cast<const c2*>(smem + (size_t)(n & 1) * kStageBytes), P, t, tw, bufB_p);
-    __syncthreads();
+    __syncthreads();                              // nobody reads bufA (or this GGSW stage) any more
     wide::inv_stage2(bufB_p, bufA_p, t, tw);
-    __syncthreads();
-    wide::inv_stage3(bufA_p, bufB_p, t, tab3i);
-    __syncthreads();
+    half_sync(P);
+    wide::inv_stage3(bufA_p, bufB_p, t);
+    half_sync(P);
     wide::phaseC_accumulate(bufB_p, t, accp);
-    __syncthreads();
+    half_sync(P);
   }
+  __syncthreads();
 
   // K4: sample extract of the constant coefficient: mask_0 = a_0, mask_j = -a_{N-j}; body = b_0
   {

@@ -32,13 +32,13 @@ namespace wide {
 
 constexpr int kThreads = 256;
 constexpr int kTwRegs = 30;                    // c2 per thread: w1f[8] w1i[7] w2f[7] w2i[8]
-constexpr int kTabC2 = kTwRegs * 128 + 32;     // + stage-3 tables [fwd/inv][p3][8]
+constexpr int kTabC2 = kTwRegs * 128;
 
 struct Tw {
   c2 w1f[8];   // exp(i pi t (1 - 4k) / 2048)                      k = 0..7
   c2 w1i[7];   // exp(+2 pi i t k / 1024)                          k = 1..7
   c2 w2f[7];   // exp(-2 pi i p2 k / 128)                          k = 1..7
-  c2 w2i[8];   // exp(+2 pi i p2 k / 128 - i pi (q2 + 8k) / 2048)  k = 0..7
+  c2 w2i[8];   // exp(+2 pi i p2 k / 128 - i pi (q2 + 8k) / 2048) / 1024   k = 0..7
 };
 
 FB_HD int swz(int idx) { return idx ^ ((idx >> 3) & 7); }
@@ -127,16 +127,35 @@ FB_HD void fwd_stage2(const c2* in, c2* out, int t, const Tw& tw) {
   for (int k = 1; k < 8; k++) out[swz(q + 64 * p + 8 * k)] = cmul(x[k], tw.w2f[k - 1]);
 }
 
-// tab3: [p3][8] twiddles of this direction (broadcast reads)
-FB_HD void fwd_stage3(const c2* in, c2* out, int t, const c2* tab3f) {
-  const int q = t & 63, p = t >> 6;
+// stage-3 twiddles depend on p3 = t >> 6 only, which is warp-uniform: compile-time constants behind a uniform branch
+// forward W16^{p3 k} = exp(-i pi p3 k / 8); inverse exp(+i pi p3 k / 8) * w^{-64 (k & 1)} (the per-parity part of
+// the untwist; see inv_stage4)
+#define FB_W3_C(k) ((k) == 1 ? 0.923879532511286756128 : (k) == 2 ? 0.707106781186547524401 : (k) == 3 ? 0.382683432365089771728 \
+                    : (k) == 5 ? -0.382683432365089771728 : (k) == 6 ? -0.707106781186547524401 : -0.923879532511286756128)
+#define FB_W3_S(k) ((k) == 1 ? 0.382683432365089771728 : (k) == 2 ? 0.707106781186547524401 : (k) == 3 ? 0.923879532511286756128 \
+                    : (k) == 5 ? 0.923879532511286756128 : (k) == 6 ? 0.707106781186547524401 : 0.382683432365089771728)
+#define FB_W3I_C(k) ((k) == 1 ? 0.956940335732208864936 : (k) == 2 ? 0.707106781186547524401 : (k) == 3 ? 0.471396736825997648556 \
+                     : (k) == 5 ? -0.290284677254462367636 : (k) == 6 ? -0.707106781186547524401 : -0.881921264348355029713)
+#define FB_W3I_S(k) ((k) == 1 ? 0.290284677254462367636 : (k) == 2 ? 0.707106781186547524401 : (k) == 3 ? 0.881921264348355029713 \
+                     : (k) == 5 ? 0.956940335732208864936 : (k) == 6 ? 0.707106781186547524401 : 0.471396736825997648556)
+
+template <int P3>
+FB_HD void fwd_stage3_p(const c2* in, c2* out, int q) {
   c2 x[8];
 #pragma unroll
-  for (int r = 0; r < 8; r++) x[r] = in[swz(q + 64 * p + 128 * r)];
+  for (int r = 0; r < 8; r++) x[r] = in[swz(q + 64 * P3 + 128 * r)];
   dft8<false>(x);
-  out[swz(q + 512 * p)] = x[0];
 #pragma unroll
-  for (int k = 1; k < 8; k++) out[swz(q + 512 * p + 64 * k)] = cmul(x[k], tab3f[8 * p + k]);
+  for (int k = 0; k < 8; k++) {
+    c2 y = x[k];
+    if (P3 == 1 && k == 4) y = rot90<false>(x[k]);
+    else if (P3 == 1 && k != 0) y = cmul(x[k], mk(FB_W3_C(k), -FB_W3_S(k)));
+    out[swz(q + 512 * P3 + 64 * k)] = y;
+  }
+}
+FB_HD void fwd_stage3(const c2* in, c2* out, int t) {
+  if ((t >> 6) == 0) fwd_stage3_p<0>(in, out, t & 63);
+  else fwd_stage3_p<1>(in, out, t & 63);
 }
 
 // forward stage 4 (a+b, a-b) of both polynomials + Fourier MAC with the staged GGSW + inverse stage 1.
@@ -189,14 +208,27 @@ FB_HD void inv_stage2(const c2* in, c2* out, int t, const Tw& tw) {
   for (int k = 0; k < 8; k++) out[swz(q + 64 * p + 8 * k)] = cmul(x[k], tw.w2i[k]);
 }
 
-FB_HD void inv_stage3(const c2* in, c2* out, int t, const c2* tab3i) {
-  const int q = t & 63, p = t >> 6;
+template <int P3>
+FB_HD void inv_stage3_p(const c2* in, c2* out, int q) {
   c2 x[8];
 #pragma unroll
-  for (int r = 0; r < 8; r++) x[r] = in[swz(q + 64 * p + 128 * r)];
+  for (int r = 0; r < 8; r++) x[r] = in[swz(q + 64 * P3 + 128 * r)];
   dft8<true>(x);
 #pragma unroll
-  for (int k = 0; k < 8; k++) out[swz(q + 512 * p + 64 * k)] = cmul(x[k], tab3i[8 * p + k]);
+  for (int k = 0; k < 8; k++) {
+    c2 y = x[k];
+    if (P3 == 0) {
+      if (k & 1) y = cmul(x[k], mk(0.995184726672196886245, -0.0980171403295606019942));   // w^-64
+    } else {
+      if (k == 4) y = rot90<true>(x[k]);
+      else if (k != 0) y = cmul(x[k], mk(FB_W3I_C(k), FB_W3I_S(k)));
+    }
+    out[swz(q + 512 * P3 + 64 * k)] = y;
+  }
+}
+FB_HD void inv_stage3(const c2* in, c2* out, int t) {
+  if ((t >> 6) == 0) inv_stage3_p<0>(in, out, t & 63);
+  else inv_stage3_p<1>(in, out, t & 63);
 }
 
 // inverse stage 4 + per-register untwist exp(-i pi m/16): torus increments of coefficients j = t + 128 m (re)
@@ -242,7 +274,7 @@ FB_HD void load_tw(Tw& tw, const c2* tab, int t) {
   for (int k = 0; k < 8; k++) tw.w2i[k] = tab[(22 + k) * 128 + t];
 }
 
-// Host-side table: [kTwRegs][128] per-thread twiddles, then tab3f[2][8], tab3i[2][8]
+// Host-side table: [kTwRegs][128] per-thread twiddles
 static inline void make_wide_table(c2* tab) {
   const long double pi = 3.141592653589793238462643383279502884L;
   auto e = [&](long double ang, long double scale) {
@@ -257,15 +289,8 @@ static inline void make_wide_table(c2* tab) {
     for (int k = 1; k < 8; k++) tab[(8 + k - 1) * 128 + t] = e(2.0L * pi * (long double)(t * k) / 1024.0L, 1.0L);
     for (int k = 1; k < 8; k++) tab[(15 + k - 1) * 128 + t] = e(-2.0L * pi * (long double)(p2 * k) / 128.0L, 1.0L);
     for (int k = 0; k < 8; k++)
-      tab[(22 + k) * 128 + t] = e(2.0L * pi * (long double)(p2 * k) / 128.0L - pi * (long double)(q2 + 8 * k) / 2048.0L, 1.0L);
+      tab[(22 + k) * 128 + t] = e(2.0L * pi * (long double)(p2 * k) / 128.0L - pi * (long double)(q2 + 8 * k) / 2048.0L, 1.0L / 1024.0L);
   }
-  c2* t3f = tab + kTwRegs * 128;
-  c2* t3i = t3f + 16;
-  for (int p = 0; p < 2; p++)
-    for (int k = 0; k < 8; k++) {
-      t3f[8 * p + k] = e(-2.0L * pi * (long double)(p * k) / 16.0L, 1.0L);
-      t3i[8 * p + k] = e(2.0L * pi * (long double)(p * k) / 16.0L - pi * (long double)(64 * (k & 1)) / 2048.0L, 1.0L / 1024.0L);
-    }
 }
 
 }  // namespace wide

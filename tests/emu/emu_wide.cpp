@@ -20,18 +20,16 @@ struct Cta {
     make_wide_table(tab.data());
     for (int tid = 0; tid < 256; tid++) load_tw(tw[tid], tab.data(), tid & 127);
   }
-  const c2* t3f() const { return tab.data() + kTwRegs * 128; }
-  const c2* t3i() const { return tab.data() + kTwRegs * 128 + 16; }
 };
 
 // stages 2 and 3 of the forward transform of both polynomials: bufA -> bufB -> bufA (barriers between the loops)
 void forward_tail(Cta& c) {
   for (int tid = 0; tid < 256; tid++) fwd_stage2(c.bufA.data() + (tid >> 7) * kHalfN, c.bufB.data() + (tid >> 7) * kHalfN, tid & 127, c.tw[tid]);
-  for (int tid = 0; tid < 256; tid++) fwd_stage3(c.bufB.data() + (tid >> 7) * kHalfN, c.bufA.data() + (tid >> 7) * kHalfN, tid & 127, c.t3f());
+  for (int tid = 0; tid < 256; tid++) fwd_stage3(c.bufB.data() + (tid >> 7) * kHalfN, c.bufA.data() + (tid >> 7) * kHalfN, tid & 127);
 }
 void inverse_tail(Cta& c) {
   for (int tid = 0; tid < 256; tid++) inv_stage2(c.bufB.data() + (tid >> 7) * kHalfN, c.bufA.data() + (tid >> 7) * kHalfN, tid & 127, c.tw[tid]);
-  for (int tid = 0; tid < 256; tid++) inv_stage3(c.bufA.data() + (tid >> 7) * kHalfN, c.bufB.data() + (tid >> 7) * kHalfN, tid & 127, c.t3i());
+  for (int tid = 0; tid < 256; tid++) inv_stage3(c.bufA.data() + (tid >> 7) * kHalfN, c.bufB.data() + (tid >> 7) * kHalfN, tid & 127);
 }
 }  // namespace
 
