@@ -85,6 +85,7 @@ def lib():
     L.fb_or_fold.argtypes = [vp, vp, sz, vp]
     L.fb_parse_debug.argtypes = [C.c_char_p, C.c_char_p, sz]
     L.fb_plan_stats.argtypes = [C.c_char_p, sz, C.POINTER(MatchStats)]
+    L.fb_plan_level_widths.argtypes = [C.c_char_p, sz, C.c_int, C.c_int, vp, sz]
     L.fb_plan_eval_plain.argtypes = [C.c_char_p, vp, sz, C.c_int, C.c_int, C.POINTER(C.c_int)]
     L.fb_kernel_stats_reset.argtypes = [vp]
     L.fb_set_latency_threshold.argtypes = [vp, C.c_int]
@@ -139,6 +140,15 @@ def plan_stats(pattern: str, n_chars: int) -> dict:
     if rc != FB_OK:
         _raise(rc, "plan failed for %r" % pattern)
     return st.as_dict()
+
+
+def plan_level_widths(pattern: str, n_chars: int, rank: int = 0, world: int = 1) -> list:
+    """PBS batch width of every level of the lowered plan (host only)"""
+    buf = np.zeros(256, dtype=np.int32)
+    n = lib().fb_plan_level_widths(pattern.encode(), n_chars, rank, world, _p(buf), buf.size)
+    if n < 0:
+        _raise(n, "plan_level_widths")
+    return [int(x) for x in buf[:min(n, buf.size)]]
 
 
 def plan_eval_plain(pattern: str, content: str, rank: int = 0, world: int = 1) -> int:

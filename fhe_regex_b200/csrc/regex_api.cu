@@ -158,6 +158,21 @@ extern "C" int fb_plan_stats(const char* pattern, size_t n_chars, fb_match_stats
   return FB_OK;
 }
 
+extern "C" int fb_plan_level_widths(const char* pattern, size_t n_chars, int rank, int world, int32_t* widths, size_t cap) {
+  if (!pattern || (!widths && cap)) return FB_ERR_ARG;
+  Plan plan;
+  std::string err;
+  int rc = build_plan(pattern, n_chars, rank, world, plan, err);
+  if (rc != FB_OK) return rc;
+  int n = 0;
+  for (auto& l : plan.levels) {
+    if (l.in_rows.empty()) continue;
+    if ((size_t)n < cap) widths[n] = (int32_t)l.in_rows.size();
+    n++;
+  }
+  return n;
+}
+
 extern "C" int fb_plan_eval_plain(const char* pattern, const uint8_t* content, size_t n_chars, int rank, int world, int* result) {
   if (!pattern || !result || (!content && n_chars)) return FB_ERR_ARG;
   Plan plan;

@@ -554,6 +554,12 @@ struct Lowering {
   std::vector<uint32_t> seen_stamp;                         // flattening scratch: value id -> generation
   uint32_t seen_gen = 0;
   bool absorb = true;                                       // drop OR operands implied by another operand (x | (x & y) = x)
+  // multi-GPU with absorption: every rank lowers the WHOLE match, absorbs globally, and keeps a contiguous slice
+  // (by leftmost content position) of the surviving operands of the final OR -- so a rank neither evaluates variants
+  // that a variant of another rank implies nor bootstraps leaves outside its slice
+  int shard_rank = 0, shard_world = 1;
+  int32_t shard_root = -1;
+  bool sharded = false;
   std::unordered_map<int32_t, std::vector<Lit>> and_sets;   // PBS node of a lowered AND -> its full literal set
   uint64_t absorbed = 0;
   std::vector<std::pair<int32_t, int32_t>> eq_parts;         // eq node -> its two nibble-test nodes (eq = their AND), or (-1,-1)
@@ -732,7 +738,25 @@ struct Lowering {
     ops.swap(kept);
   }
 
+  // this rank's contiguous slice of the final OR's operands, ordered by the leftmost content position they read
+  void shard_operands(std::vector<Lit>& ops) {
+    std::vector<std::pair<int64_t, Lit>> keyed;
+    keyed.reserve(ops.size());
+    for (auto& l : ops) {
+      auto it = node_shape.find(l.node);
+      keyed.emplace_back(it == node_shape.end() ? (int64_t)INT32_MAX : (int64_t)it->second.second, l);
+    }
+    std::stable_sort(keyed.begin(), keyed.end(), [](const std::pair<int64_t, Lit>& a, const std::pair<int64_t, Lit>& b) { return a.first < b.first; });
+    const size_t n = keyed.size();
+    const size_t lo = n * (size_t)shard_rank / (size_t)shard_world, hi = n * ((size_t)shard_rank + 1) / (size_t)shard_world;
+    std::vector<Lit> mine;
+    for (size_t i = lo; i < hi; i++) mine.push_back(keyed[i].second);
+    std::sort(mine.begin(), mine.end(), [](const Lit& x, const Lit& y) { return x.node < y.node || (x.node == y.node && x.neg < y.neg); });
+    ops.swap(mine);
+  }
+
   LitOrConst lower(int32_t root) {
+    if (shard_world > 1) shard_root = root;
     // iterative post-order over the value DAG (the sequential OR fold is tens of thousands deep)
     std::vector<int32_t> stack{root};
     while (!stack.empty()) {
@@ -833,6 +857,11 @@ struct Lowering {
       }
       if (lits.empty()) { lowered[v] = LitOrConst{is_and ? 1 : 0, {0, false}}; stack.pop_back(); continue; }
       if (!is_and && absorb && lits.size() > 1) absorb_or_operands(lits);
+      if (!is_and && v == shard_root && shard_world > 1) {
+        shard_operands(lits);
+        sharded = true;
+        if (lits.empty()) { lowered[v] = LitOrConst{0, {0, false}}; stack.pop_back(); continue; }
+      }
       const std::vector<Lit> full = lits;
       // one sum-then-LUT node takes up to 15 literals: shared run blocks are only worth a level beyond that
       if (is_and && lits.size() > 15) lits = compress_runs(lits, 3);
@@ -997,8 +1026,10 @@ int build_plan(const std::string& pattern, size_t n_chars, int rank, int world, 
   try {
     Builder B(n_chars);
     std::vector<int32_t> branches;
+    const bool absorb = std::getenv("FB_PLAN_NO_ABSORB") == nullptr;   // reference-shaped plan (every variant evaluated) when set
+    const bool shard_at_root = absorb && world > 1;                    // see Lowering::shard_operands
     for (size_t i = 0; i < n_chars; i++) {  // engine.rs:15-18
-      if ((int)(i % (size_t)world) != rank) continue;
+      if (!shard_at_root && (int)(i % (size_t)world) != rank) continue;
       for (auto& b : B.build(re, i)) branches.push_back(b.first);
     }
     Execution ex;
@@ -1014,8 +1045,11 @@ int build_plan(const std::string& pattern, size_t n_chars, int rank, int world, 
       }
     }
     Lowering L(ex, n_chars);
-    L.absorb = std::getenv("FB_PLAN_NO_ABSORB") == nullptr;   // reference-shaped plan (every variant evaluated) when set
+    L.absorb = absorb;
+    if (shard_at_root) { L.shard_rank = rank; L.shard_world = world; }
     LitOrConst out = L.lower(res.val);
+    // no final OR to slice (a single variant, a constant): rank 0 owns the whole result
+    if (shard_at_root && !L.sharded && rank != 0) out = LitOrConst{0, {0, false}};
     plan = Plan();
     emit_plan(L, out, n_chars, plan);
     plan.stats.variants = branches.size();

@@ -117,6 +117,10 @@ int fb_parse_debug(const char* pattern, char* out, size_t cap);
  * fills variants / ct_ops / cache_hits / ops_* / pbs / levels / max_level_width. */
 int fb_plan_stats(const char* pattern, size_t n_chars, fb_match_stats* stats);
 
+/* PBS batch width of every level of the lowered plan (host only): returns the number of levels (>= 0, may
+ * exceed cap; only cap entries are written) or a negative error code */
+int fb_plan_level_widths(const char* pattern, size_t n_chars, int rank, int world, int32_t* widths, size_t cap);
+
 /* plaintext dry run of the lowered circuit on cleartext content bytes (host only, no ciphertexts):
  * result = what decrypt(has_match(..)) would give for this rank's share; used to test the lowering. */
 int fb_plan_eval_plain(const char* pattern, const uint8_t* content, size_t n_chars, int rank, int world, int* result);
