@@ -50,6 +50,7 @@ extern "C" int fb_ctx_create(fb_ctx** out, int device) {
   fb_ctx* ctx = new (std::nothrow) fb_ctx();
   if (!ctx) return FB_ERR_ARG;
   ctx->device = device;
+  ctx->quantum = prop.multiProcessorCount * fb::br_samples_per_cta();
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete ctx;
     g_create_err = "cudaSetDevice / cudaStreamCreate failed";
@@ -163,9 +164,7 @@ extern "C" int fb_measure_fp64_peak(fb_ctx* ctx, int reps, double* tflops) {
 // batch sizes that fill the GPU evenly are multiples of this (SM count x samples per CTA)
 extern "C" int fb_pbs_batch_quantum(fb_ctx* ctx) {
   if (!ctx) return FB_ERR_ARG;
-  cudaDeviceProp prop;
-  if (cudaGetDeviceProperties(&prop, ctx->device) != cudaSuccess) return FB_ERR_CUDA;
-  return prop.multiProcessorCount * fb::br_samples_per_cta();
+  return ctx->quantum;
 }
 
 // ---- timed launches ---------------------------------------------------------------------------
@@ -204,10 +203,21 @@ int fb_run_blind_rotate(fb_ctx* ctx, const uint64_t* d_small, const uint64_t* d_
   fb_event_pair ev;
   bool t = timing_begin(ctx, 1, ev);
   // a level narrower than two waves of SMs is latency: one PBS per CTA (br_wide.cu); otherwise throughput
-  // (kernels.cu, up to 4 PBS per CTA)
-  cudaError_t e = (count <= ctx->wide_max)
-                      ? fb::launch_blind_rotate_wide(ctx->d_fbsk, d_small, d_luts, d_lut_idx, d_out, d_out_rows, ctx->d_wtab, count, ctx->stream)
-                      : fb::launch_blind_rotate(ctx->d_fbsk, d_small, d_luts, d_lut_idx, d_out, d_out_rows, ctx->d_tabs, count, ctx->stream);
+  // (kernels.cu, up to 4 PBS per CTA).  A short tail behind full throughput waves (e.g. 620 = 592 + 28) would
+  // cost a whole extra throughput wave: it goes to the latency kernel instead.
+  cudaError_t e;
+  if (count <= ctx->wide_max) {
+    e = fb::launch_blind_rotate_wide(ctx->d_fbsk, d_small, d_luts, d_lut_idx, d_out, d_out_rows, ctx->d_wtab, count, ctx->stream);
+  } else {
+    const int q = ctx->quantum;
+    const int tail = (q > 0) ? count % q : 0;
+    const int head = (tail > 0 && tail <= ctx->wide_max) ? count - tail : count;
+    e = fb::launch_blind_rotate(ctx->d_fbsk, d_small, d_luts, d_lut_idx, d_out, d_out_rows, ctx->d_tabs, head, ctx->stream);
+    if (e == cudaSuccess && head < count)
+      e = fb::launch_blind_rotate_wide(ctx->d_fbsk, d_small + (size_t)head * FB_LWE_SMALL_WORDS, d_luts, d_lut_idx + head,
+                                       d_out_rows ? d_out : d_out + (size_t)head * FB_LWE_BIG_WORDS,
+                                       d_out_rows ? d_out_rows + head : nullptr, ctx->d_wtab, tail, ctx->stream);
+  }
   timing_end(ctx, t, ev);
   if (e != cudaSuccess) return fb_cuda_fail(ctx, e, "blind_rotate_kernel launch");
   ctx->ks.br_launches++;

@@ -30,6 +30,7 @@ struct fb_ctx {
   fb::c2* d_fbsk = nullptr;
   fb::c2* d_tabs = nullptr;
   fb::c2* d_wtab = nullptr;    // table of the latency blind rotation (inside the d_tabs allocation)
+  int quantum = 592;           // SM count x PBS per CTA of the throughput blind rotation
   int wide_max = 296;          // batches up to this many PBS take the latency kernel (env FB_WIDE_MAX; 0 = never)
   bool have_key = false;
   // scratch for the batch entry points

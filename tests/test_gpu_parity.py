@@ -73,10 +73,12 @@ def test_fourier_key_matches_emulation(server_key, gpu_key):
     assert np.abs(got - exp).max() < 1e-11 * scale
 
 
-@pytest.fixture(params=["latency", "throughput"])
+@pytest.fixture(params=["latency", "throughput", "default"])
 def br_variant(request, gpu_key):
-    """small batches through both blind rotations: one PBS per CTA (br_wide.cu) / up to 4 per CTA (kernels.cu)"""
-    prev = gpu_key.set_latency_threshold(0 if request.param == "throughput" else 1 << 30)
+    """batches through both blind rotations: one PBS per CTA (br_wide.cu) / up to 4 per CTA (kernels.cu) / the
+    default dispatch (latency kernel up to 296 PBS and for short tails behind full throughput waves)"""
+    thr = {"latency": 1 << 30, "throughput": 0, "default": 296}[request.param]
+    prev = gpu_key.set_latency_threshold(thr)
     yield request.param
     gpu_key.set_latency_threshold(prev)
 
@@ -130,7 +132,7 @@ def test_bootstrap_stagewise_against_oracle(client_key, server_key, gpu_key, br_
     assert np.abs(err).max() < PBS_ERR_MAX
 
 
-@pytest.mark.parametrize("count", [1, 2, 74, 75, 148, 149, 296, 297, 444, 445, 592, 593, 1185])
+@pytest.mark.parametrize("count", [1, 2, 74, 75, 148, 149, 296, 297, 444, 445, 592, 593, 620, 1185])
 def test_bootstrap_batch_size_boundaries(count, fck, gpu_key, br_variant):
     # the throughput blind rotation picks 1..4 samples per SM from the batch size (ragged last CTAs at every
     # boundary); the latency one runs in waves of one CTA per PBS
