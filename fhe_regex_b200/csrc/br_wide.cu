@@ -12,6 +12,7 @@
 // switches to 0 (all of them for trivial inputs) are skipped through a compacted step list.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "br_wide.cuh"
 #include "kernels.h"
 #include "ptx_sync.cuh"
@@ -35,7 +36,7 @@ __device__ __forceinline__ void half_sync(int P) { asm volatile("bar.sync %0, 12
 __global__ void __launch_bounds__(wide::kThreads, 1)
 blind_rotate_wide_kernel(const c2* __restrict__ fbsk, const uint64_t* __restrict__ small, const uint64_t* __restrict__ luts,
                          const uint32_t* __restrict__ lut_idx, uint64_t* __restrict__ out, const int32_t* __restrict__ out_rows,
-                         const c2* __restrict__ wtab, int count) {
+                         const c2* __restrict__ wtab, int count, int skew_cycles) {
   extern __shared__ __align__(128) unsigned char smem[];
   c2* bufA = reinterpret_cast<c2*>(smem + kOffBufA);
   c2* bufB = reinterpret_cast<c2*>(smem + kOffBufB);
@@ -114,6 +115,12 @@ blind_rotate_wide_kernel(const c2* __restrict__ fbsk, const uint64_t* __restrict
     mbar_wait(full_bar + (n & 1), (uint32_t)(n >> 1) & 1u);
     wide::mac_inv_stage1(bufA, bufA + kHalfN, reinterpret_cast<const c2*>(smem + (size_t)(n & 1) * kStageBytes), P, t, tw, bufB_p);
     __syncthreads();                              // nobody reads bufA (or this GGSW stage) any more
+    // the halves leave this barrier in phase; holding one back by a fraction of a stage makes its shared-memory
+    // bursts fall into the other half's arithmetic for the six per-half stages until they meet again
+    if (P == 1 && skew_cycles > 0) {
+      const long long t0 = clock64();
+      while (clock64() - t0 < (long long)skew_cycles) {}
+    }
     wide::inv_stage2(bufB_p, bufA_p, t, tw);
     half_sync(P);
     wide::inv_stage3(bufA_p, bufB_p, t);
@@ -142,12 +149,14 @@ cudaError_t launch_blind_rotate_wide(const c2* fbsk, const uint64_t* small, cons
                                      uint64_t* out, const int32_t* out_rows, const c2* wtab, int count, cudaStream_t st) {
   if (count <= 0) return cudaSuccess;
   static bool configured = false;
+  static int skew = 200;   // cycles; measured on B200: 0 -> 2.46 ms, 100..300 -> 2.38-2.40 ms per 148-PBS wave
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(blind_rotate_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWideSmem);
     if (e != cudaSuccess) return e;
     configured = true;
+    if (const char* e2 = getenv("FB_WIDE_SKEW")) skew = atoi(e2);
   }
-  blind_rotate_wide_kernel<<<count, wide::kThreads, kWideSmem, st>>>(fbsk, small, luts, lut_idx, out, out_rows, wtab, count);
+  blind_rotate_wide_kernel<<<count, wide::kThreads, kWideSmem, st>>>(fbsk, small, luts, lut_idx, out, out_rows, wtab, count, skew);
   return cudaGetLastError();
 }
 
