@@ -173,7 +173,10 @@ def run_reference(args, rank: int):
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }), flush=True)
+    }), file=_JSON_OUT, flush=True)
+
+
+_JSON_OUT = sys.stdout
 
 
 def main():
@@ -187,6 +190,12 @@ def main():
     ap.add_argument("--no-match", action="store_true")
     ap.add_argument("--cpu-samples", type=int, default=0)
     args = ap.parse_args()
+
+    # exactly ONE line on stdout: libraries (NCCL prints its version banner to stdout) get stderr instead
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.impl == "reference":
@@ -390,7 +399,7 @@ def main():
                                     "single_thread_value": v1}
         else:
             line["cpu_baseline"] = None
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -3,6 +3,8 @@
 // behaviour (incl. its quirks), not from its code: the reference evaluates Rc closures
 // against deep-cloned provenance trees; here variants are integer thunks and provenance is hash-consed.
 #include "regex_host.h"
+#include <chrono>
+#include <cstdio>
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -693,7 +695,10 @@ struct Lowering {
   // that starts at i+L-1 with run length 1.  Sets are sorted literal lists; candidates are visited by
   // increasing size and looked up through the kept sets indexed by their rarest literal.
   static uint64_t lit_key(const Lit& l) { return ((uint64_t)(uint32_t)l.node << 1) | (l.neg ? 1u : 0u); }
+  double absorb_ms = 0;
   void absorb_or_operands(std::vector<Lit>& ops) {
+    const auto t_begin = std::chrono::steady_clock::now();
+    struct Guard { double& acc; std::chrono::steady_clock::time_point t; ~Guard() { acc += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); } } guard{absorb_ms, t_begin};
     struct Item { std::vector<uint64_t> set; Lit lit; };
     std::vector<Item> items;
     items.reserve(ops.size());
@@ -736,6 +741,68 @@ struct Lowering {
     }
     std::sort(kept.begin(), kept.end(), [](const Lit& x, const Lit& y) { return x.node < y.node || (x.node == y.node && x.neg < y.neg); });
     ops.swap(kept);
+  }
+
+  // Absorption on the VALUE level, before any operand of a wide OR is lowered: an operand that is an AND over a
+  // superset of another operand's conjuncts is implied by it and is neither lowered nor kept (for the 256-character
+  // /a+b?c/ this spares lowering 64 771 of the 65 025 variants; sound for the same reason as absorb_or_operands).
+  // Sets are sorted value ids; candidates go by increasing size against kept sets indexed by their rarest member.
+  std::unordered_map<int32_t, std::vector<int32_t>> pre_absorbed;   // OR value -> surviving operand values
+  const std::vector<int32_t>& pre_absorb(int32_t v, const std::vector<int32_t>& ops) {
+    auto cached = pre_absorbed.find(v);
+    if (cached != pre_absorbed.end()) return cached->second;
+    const auto t_begin = std::chrono::steady_clock::now();
+    const size_t nv = ex.vals.items.size();
+    std::vector<std::vector<int32_t>> sets(ops.size());
+    std::vector<char> dead(ops.size(), 0);
+    std::vector<uint32_t> freq(nv, 0);
+    std::vector<int32_t> work;
+    for (size_t o = 0; o < ops.size(); o++) {
+      auto& set = sets[o];
+      if (ex.vals.items[ops[o]].t != V_AND) { set.push_back(ops[o]); }
+      else {
+        work.assign(1, ops[o]);
+        while (!work.empty()) {
+          const int32_t x = work.back();
+          work.pop_back();
+          const Triple tx = ex.vals.items[x];
+          if (tx.t == V_AND) { work.push_back(tx.a); work.push_back(tx.b); continue; }
+          if (tx.t == V_CONST) {
+            if (tx.a & 1) continue;          // neutral conjunct
+            dead[o] = 1;                     // a false conjunct: the operand is false, neutral in the OR
+            break;
+          }
+          set.push_back(x);
+        }
+        std::sort(set.begin(), set.end());
+        set.erase(std::unique(set.begin(), set.end()), set.end());
+      }
+      if (!dead[o]) for (int32_t x : set) freq[x]++;
+    }
+    std::vector<uint32_t> order;
+    for (size_t o = 0; o < ops.size(); o++) if (!dead[o]) order.push_back((uint32_t)o);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return sets[a].size() < sets[b].size(); });
+    std::vector<std::vector<uint32_t>> by_rare(nv);
+    std::vector<char> keep(ops.size(), 0);
+    for (uint32_t o : order) {
+      const auto& B = sets[o];
+      bool implied = B.empty() ? false : false;
+      for (size_t bi = 0; bi < B.size() && !implied; bi++)
+        for (uint32_t a : by_rare[B[bi]]) {
+          const auto& A = sets[a];
+          if (A.size() <= B.size() && std::includes(B.begin(), B.end(), A.begin(), A.end())) { implied = true; break; }
+        }
+      if (implied) { absorbed++; continue; }
+      keep[o] = 1;
+      if (B.empty()) continue;               // an empty conjunction is the constant true: the lowering decides the OR
+      int32_t rare = B[0];
+      for (int32_t x : B) if (freq[x] < freq[rare]) rare = x;
+      by_rare[rare].push_back(o);
+    }
+    std::vector<int32_t> out;
+    for (size_t o = 0; o < ops.size(); o++) if (keep[o]) out.push_back(ops[o]);
+    absorb_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    return pre_absorbed.emplace(v, std::move(out)).first->second;
   }
 
   // this rank's contiguous slice of the final OR's operands, ordered by the leftmost content position they read
@@ -806,11 +873,13 @@ struct Lowering {
           const Triple tx = ex.vals.items[x];
           if (tx.t == t.t) { work.push_back(tx.a); work.push_back(tx.b); continue; }
           ops.push_back(x);
-          if (!is_lowered(x)) { stack.push_back(x); missing = true; }
         }
       }
-      if (missing) continue;
       const bool is_and = t.t == V_AND;
+      if (!is_and && absorb && ops.size() > 16) ops = pre_absorb(v, ops);
+      for (int32_t x : ops)
+        if (!is_lowered(x)) { stack.push_back(x); missing = true; }
+      if (missing) continue;
       std::vector<Lit> lits;
       bool decided = false;
       // operand literals: drop neutral constants, dedupe (idempotence), detect x & !x / x | !x
@@ -1024,6 +1093,9 @@ int build_plan(const std::string& pattern, size_t n_chars, int rank, int world, 
   if (rc != FB_OK) return rc;
   if (world < 1 || rank < 0 || rank >= world) { err = "bad rank/world"; return FB_ERR_ARG; }
   try {
+    const bool timing = std::getenv("FB_PLAN_TIMING") != nullptr;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
     Builder B(n_chars);
     std::vector<int32_t> branches;
     const bool absorb = std::getenv("FB_PLAN_NO_ABSORB") == nullptr;   // reference-shaped plan (every variant evaluated) when set
@@ -1032,6 +1104,7 @@ int build_plan(const std::string& pattern, size_t n_chars, int rank, int world, 
       if (!shard_at_root && (int)(i % (size_t)world) != rank) continue;
       for (auto& b : B.build(re, i)) branches.push_back(b.first);
     }
+    const double t1 = now();
     Execution ex;
     ThunkEval ev(B, ex);
     Res res;
@@ -1044,14 +1117,19 @@ int build_plan(const std::string& pattern, size_t n_chars, int rank, int world, 
         res = ex.ct_or(res, br);
       }
     }
+    const double t2 = now();
     Lowering L(ex, n_chars);
     L.absorb = absorb;
     if (shard_at_root) { L.shard_rank = rank; L.shard_world = world; }
     LitOrConst out = L.lower(res.val);
     // no final OR to slice (a single variant, a constant): rank 0 owns the whole result
     if (shard_at_root && !L.sharded && rank != 0) out = LitOrConst{0, {0, false}};
+    const double t3 = now();
     plan = Plan();
     emit_plan(L, out, n_chars, plan);
+    if (timing)
+      fprintf(stderr, "[plan] enumerate %.1f ms, evaluate (executor bookkeeping) %.1f ms, lower %.1f ms (absorption %.1f ms), emit %.1f ms\n",
+              t1 - t0, t2 - t1, t3 - t2, L.absorb_ms, now() - t3);
     plan.stats.variants = branches.size();
     plan.stats.ct_ops = ex.ct_ops;
     plan.stats.cache_hits = ex.cache_hits;
