@@ -89,6 +89,7 @@ def lib():
     L.fb_plan_eval_plain.argtypes = [C.c_char_p, vp, sz, C.c_int, C.c_int, C.POINTER(C.c_int)]
     L.fb_kernel_stats_reset.argtypes = [vp]
     L.fb_set_latency_threshold.argtypes = [vp, C.c_int]
+    L.fb_set_cluster_threshold.argtypes = [vp, C.c_int]
     L.fb_kernel_stats_get.argtypes = [vp, C.POINTER(KernelStats)]
     L.fb_kernel_timing_enable.argtypes = [vp, C.c_int]
     L.fb_measure_fp64_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
@@ -334,6 +335,13 @@ class ServerKey:
     def set_latency_threshold(self, max_count: int) -> int:
         """batches of up to max_count PBS use the one-PBS-per-CTA blind rotation; returns the previous value"""
         prev = lib().fb_set_latency_threshold(self._h, int(max_count))
+        if prev < 0:
+            self._check(prev)
+        return prev
+
+    def set_cluster_threshold(self, max_count: int) -> int:
+        """batches of up to max_count PBS use the one-PBS-per-SM-pair blind rotation; returns the previous value"""
+        prev = lib().fb_set_cluster_threshold(self._h, int(max_count))
         if prev < 0:
             self._check(prev)
         return prev

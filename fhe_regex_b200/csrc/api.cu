@@ -59,10 +59,14 @@ extern "C" int fb_ctx_create(fb_ctx** out, int device) {
   // twiddle tables
   // (the table of the latency kernel rides behind the two 12x32 tables of the throughput kernel)
   const size_t n_tabs = 2 * fb::kTabEntries * 32;
-  std::vector<c2> tabs(n_tabs + fb::br_wide_table_bytes() / sizeof(c2));
+  const size_t n_wide = fb::br_wide_table_bytes() / sizeof(c2);
+  std::vector<c2> tabs(n_tabs + n_wide + fb::br_duo_table_bytes() / sizeof(c2));
   fb::make_twiddle_tables(tabs.data(), tabs.data() + fb::kTabEntries * 32);
   fb::br_wide_make_table(tabs.data() + n_tabs);
+  fb::br_duo_make_table(tabs.data() + n_tabs + n_wide);
   if (const char* w = std::getenv("FB_WIDE_MAX")) ctx->wide_max = std::atoi(w);
+  ctx->duo_max = fb::br_duo_max_clusters();
+  if (const char* w = std::getenv("FB_DUO_MAX")) ctx->duo_max = std::atoi(w);
   if (cudaMalloc(&ctx->d_tabs, tabs.size() * sizeof(c2)) != cudaSuccess ||
       cudaMemcpy(ctx->d_tabs, tabs.data(), tabs.size() * sizeof(c2), cudaMemcpyHostToDevice) != cudaSuccess) {
     delete ctx;
@@ -70,6 +74,7 @@ extern "C" int fb_ctx_create(fb_ctx** out, int device) {
     return FB_ERR_CUDA;
   }
   ctx->d_wtab = ctx->d_tabs + n_tabs;
+  ctx->d_dtab = ctx->d_wtab + n_wide;
   *out = ctx;
   return FB_OK;
 }
@@ -205,18 +210,24 @@ int fb_run_blind_rotate(fb_ctx* ctx, const uint64_t* d_small, const uint64_t* d_
   // a level narrower than two waves of SMs is latency: one PBS per CTA (br_wide.cu); otherwise throughput
   // (kernels.cu, up to 4 PBS per CTA).  A short tail behind full throughput waves (e.g. 620 = 592 + 28) would
   // cost a whole extra throughput wave: it goes to the latency kernel instead.
+  // Narrower still -- at most as many PBS as the device runs CTA pairs -- a PBS gets two SMs (br_duo.cu).
+  auto narrow = [&](const uint64_t* sm, const uint32_t* li, uint64_t* o, const int32_t* orows, int n) {
+    return (n <= ctx->duo_max)
+               ? fb::launch_blind_rotate_duo(ctx->d_fbsk, sm, d_luts, li, o, orows, ctx->d_dtab, n, ctx->stream)
+               : fb::launch_blind_rotate_wide(ctx->d_fbsk, sm, d_luts, li, o, orows, ctx->d_wtab, n, ctx->stream);
+  };
+  const int narrow_max = ctx->wide_max > ctx->duo_max ? ctx->wide_max : ctx->duo_max;
   cudaError_t e;
-  if (count <= ctx->wide_max) {
-    e = fb::launch_blind_rotate_wide(ctx->d_fbsk, d_small, d_luts, d_lut_idx, d_out, d_out_rows, ctx->d_wtab, count, ctx->stream);
+  if (count <= narrow_max) {
+    e = narrow(d_small, d_lut_idx, d_out, d_out_rows, count);
   } else {
     const int q = ctx->quantum;
     const int tail = (q > 0) ? count % q : 0;
-    const int head = (tail > 0 && tail <= ctx->wide_max) ? count - tail : count;
+    const int head = (tail > 0 && tail <= narrow_max) ? count - tail : count;
     e = fb::launch_blind_rotate(ctx->d_fbsk, d_small, d_luts, d_lut_idx, d_out, d_out_rows, ctx->d_tabs, head, ctx->stream);
     if (e == cudaSuccess && head < count)
-      e = fb::launch_blind_rotate_wide(ctx->d_fbsk, d_small + (size_t)head * FB_LWE_SMALL_WORDS, d_luts, d_lut_idx + head,
-                                       d_out_rows ? d_out : d_out + (size_t)head * FB_LWE_BIG_WORDS,
-                                       d_out_rows ? d_out_rows + head : nullptr, ctx->d_wtab, tail, ctx->stream);
+      e = narrow(d_small + (size_t)head * FB_LWE_SMALL_WORDS, d_lut_idx + head, d_out_rows ? d_out : d_out + (size_t)head * FB_LWE_BIG_WORDS,
+                 d_out_rows ? d_out_rows + head : nullptr, tail);
   }
   timing_end(ctx, t, ev);
   if (e != cudaSuccess) return fb_cuda_fail(ctx, e, "blind_rotate_kernel launch");
@@ -257,6 +268,12 @@ extern "C" int fb_set_latency_threshold(fb_ctx* ctx, int max_count) {
   if (!ctx || max_count < 0) return FB_ERR_ARG;
   const int prev = ctx->wide_max;
   ctx->wide_max = max_count;
+  return prev;
+}
+extern "C" int fb_set_cluster_threshold(fb_ctx* ctx, int max_count) {
+  if (!ctx || max_count < 0) return FB_ERR_ARG;
+  const int prev = ctx->duo_max;
+  ctx->duo_max = max_count;
   return prev;
 }
 extern "C" int fb_kernel_stats_reset(fb_ctx* ctx) {

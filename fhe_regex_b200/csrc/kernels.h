@@ -14,6 +14,12 @@ size_t br_wide_table_bytes();
 void br_wide_make_table(c2* host_tab);
 cudaError_t launch_blind_rotate_wide(const c2* fbsk, const uint64_t* small, const uint64_t* luts, const uint32_t* lut_idx,
                                      uint64_t* out, const int32_t* out_rows, const c2* wtab, int count, cudaStream_t st);
+// cluster variant: one PBS per pair of CTAs (br_duo.cu)
+size_t br_duo_table_bytes();
+void br_duo_make_table(c2* host_tab);
+cudaError_t launch_blind_rotate_duo(const c2* fbsk, const uint64_t* small, const uint64_t* luts, const uint32_t* lut_idx,
+                                    uint64_t* out, const int32_t* out_rows, const c2* dtab, int count, cudaStream_t st);
+int br_duo_max_clusters();
 cudaError_t launch_lincomb(uint64_t* arena, const int32_t* out_rows, const int32_t* term_off, const int32_t* term_rows,
                            const int64_t* term_coef, const uint64_t* body_const, int n_out, cudaStream_t st);
 // keyswitch as an int8 tensor-core contraction (ks_kernels.cu)

@@ -141,3 +141,66 @@ def test_wide_trivial_input_is_exact(emu_wide, emu_fbsk, server_key):
     emu_wide.emu_wide_blind_rotate(_p(emu_fbsk), _p(small), _p(lut), _p(acc), -1)
     ref = tfhe.bootstrap_small(server_key, small, lut)
     assert (tfhe.sample_extract(acc) == ref).all()
+
+
+# ---- cluster variant (one sample per pair of CTAs, fhe_regex_b200/csrc/br_duo.cuh) ---------------------------
+
+@pytest.fixture(scope="module")
+def emu_duo():
+    so = os.path.join(EMU_DIR, "libemu_duo.so")
+    srcs = [os.path.join(EMU_DIR, "emu_duo.cpp"), os.path.join(CSRC, "br_duo.cuh"), os.path.join(CSRC, "br_core.cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(s) for s in srcs):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-march=x86-64-v3", "-fPIC", "-shared", "-o", so, srcs[0]])
+    return ctypes.CDLL(so)
+
+
+def test_duo_spectrum_equals_key_conversion_order(emu_duo, emu_fbsk, server_key):
+    bsk = server_key.bsk.reshape(742, 2, 2, 2048)
+    for (i, r, c) in ((0, 0, 0), (5, 1, 1), (741, 0, 1)):
+        spec = np.zeros((1024, 2), dtype=np.float64)
+        emu_duo.emu_duo_forward_torus(_p(np.ascontiguousarray(bsk[i, r, c])), _p(spec))
+        ref = emu_fbsk[i, r, c]
+        scale = np.abs(ref).max()
+        assert np.abs(spec - ref).max() < 1e-12 * scale, (i, r, c, np.abs(spec - ref).max(), scale)
+
+
+def test_duo_negacyclic_product_matches_exact(emu_duo):
+    rng = np.random.default_rng(5)
+    a = rng.integers(-(1 << 22), 1 << 22, size=2048, dtype=np.int64)
+    b = rng.integers(0, 1 << 64, size=2048, dtype=np.uint64)
+    got = np.zeros(2048, dtype=np.uint64)
+    emu_duo.emu_duo_negacyclic_mul(_p(a), _p(b), _p(got))
+    ai, bi = [int(x) for x in a], [int(x) for x in b]
+    for j in (0, 1, 7, 255, 256, 1023, 1024, 1500, 2047):
+        s = 0
+        for t in range(2048):
+            u = j - t
+            s += ai[t] * bi[u] if u >= 0 else -ai[t] * bi[u + 2048]
+        err = tfhe.torus_err(np.array([got[j]], dtype=np.uint64), np.array([s % (1 << 64)], dtype=np.uint64))[0]
+        assert abs(err) < 2 ** -20, (j, err)
+
+
+def test_duo_blind_rotate_decrypts_like_the_oracle(emu_duo, emu_fbsk, client_key, server_key):
+    msgs = np.array([6, 9], dtype=np.int64)
+    cts = tfhe.encrypt_batch(client_key, msgs, seed=79)
+    small = tfhe.keyswitch(server_key, cts)
+    lut = tfhe.make_lut(lambda x: (x * 5 + 3) % 16)
+    for b in range(len(msgs)):
+        acc = np.zeros(2 * 2048, dtype=np.uint64)
+        emu_duo.emu_duo_blind_rotate(_p(emu_fbsk), _p(small[b]), _p(lut), _p(acc), -1)
+        out = tfhe.sample_extract(acc)
+        exp = (int(msgs[b]) * 5 + 3) % 16
+        assert tfhe.decrypt_shortint(client_key, out) == exp
+        ph = tfhe.phase_batch(client_key.big, out[None])
+        err = tfhe.torus_err(ph, np.array([exp << 59], dtype=np.uint64))
+        assert np.abs(err).max() < 4e-4, err
+
+
+def test_duo_trivial_input_is_exact(emu_duo, emu_fbsk, server_key):
+    lut = tfhe.make_lut(lambda x: (7 * x + 1) % 16)
+    small = np.zeros(743, dtype=np.uint64)
+    small[742] = np.uint64(13 << 59)
+    acc = np.zeros(2 * 2048, dtype=np.uint64)
+    emu_duo.emu_duo_blind_rotate(_p(emu_fbsk), _p(small), _p(lut), _p(acc), -1)
+    ref = tfhe.bootstrap_small(server_key, small, lut)
+    assert (tfhe.sample_extract(acc) == ref).all()

@@ -73,14 +73,36 @@ def test_fourier_key_matches_emulation(server_key, gpu_key):
     assert np.abs(got - exp).max() < 1e-11 * scale
 
 
-@pytest.fixture(params=["latency", "throughput", "default"])
+BR_VARIANTS = {   # name -> (cluster threshold, latency threshold); None = leave the default
+    "cluster": (1 << 30, 0),         # one PBS per pair of SMs (br_duo.cu)
+    "latency": (0, 1 << 30),         # one PBS per CTA (br_wide.cu)
+    "throughput": (0, 0),            # up to 4 PBS per CTA (kernels.cu)
+    "default": (None, None),         # dispatch by batch size, short tails behind full throughput waves included
+}
+
+
+class _Variant:
+    def __init__(self, key, name):
+        self.key, self.name = key, name
+
+    def __enter__(self):
+        c, l = BR_VARIANTS[self.name]
+        self.prev_c = self.key.set_cluster_threshold(c) if c is not None else None
+        self.prev_l = self.key.set_latency_threshold(l) if l is not None else None
+        return self.name
+
+    def __exit__(self, *exc):
+        if self.prev_c is not None:
+            self.key.set_cluster_threshold(self.prev_c)
+        if self.prev_l is not None:
+            self.key.set_latency_threshold(self.prev_l)
+
+
+@pytest.fixture(params=list(BR_VARIANTS))
 def br_variant(request, gpu_key):
-    """batches through both blind rotations: one PBS per CTA (br_wide.cu) / up to 4 per CTA (kernels.cu) / the
-    default dispatch (latency kernel up to 296 PBS and for short tails behind full throughput waves)"""
-    thr = {"latency": 1 << 30, "throughput": 0, "default": 296}[request.param]
-    prev = gpu_key.set_latency_threshold(thr)
-    yield request.param
-    gpu_key.set_latency_threshold(prev)
+    """the same batches through the three blind rotations and through the default dispatch"""
+    with _Variant(gpu_key, request.param) as name:
+        yield name
 
 
 def test_bootstrap_trivial_inputs_bit_exact(server_key, gpu_key, br_variant):
@@ -136,8 +158,8 @@ def test_bootstrap_stagewise_against_oracle(client_key, server_key, gpu_key, br_
 def test_bootstrap_batch_size_boundaries(count, fck, gpu_key, br_variant):
     # the throughput blind rotation picks 1..4 samples per SM from the batch size (ragged last CTAs at every
     # boundary); the latency one runs in waves of one CTA per PBS
-    if br_variant == "latency" and count > 445:
-        pytest.skip("latency variant is never chosen for wide batches")
+    if br_variant in ("latency", "cluster") and count > 445:
+        pytest.skip("the narrow-level variants are never chosen for wide batches")
     msgs = (np.arange(count) * 7 + 3) % 16
     base = fck.encrypt_blocks(msgs[:min(count, 96)], seed=77)
     cts = np.ascontiguousarray(np.tile(base, ((count + 95) // 96, 1))[:count])
@@ -151,7 +173,7 @@ def test_bootstrap_batch_size_boundaries(count, fck, gpu_key, br_variant):
         assert fck.decrypt_block(out[i]) == fs[int(idx[i])](int(msgs[i])) & 15, (count, i)
 
 
-def test_latency_and_throughput_variants_agree(client_key, gpu_key):
+def test_blind_rotation_variants_agree(client_key, gpu_key):
     """same keyswitched inputs through both blind rotations: same decryptions, outputs within FFT rounding"""
     n = 150
     msgs = np.arange(n) % 16
@@ -160,12 +182,9 @@ def test_latency_and_throughput_variants_agree(client_key, gpu_key):
     luts = np.stack([tfhe.make_lut(f) for f in fs])
     idx = (np.arange(n) % 2).astype(np.uint32)
     outs = {}
-    for name, thr in (("latency", 1 << 30), ("throughput", 0)):
-        prev = gpu_key.set_latency_threshold(thr)
-        try:
+    for name in ("cluster", "latency", "throughput"):
+        with _Variant(gpu_key, name):
             outs[name] = gpu_key.pbs(cts, luts, idx)
-        finally:
-            gpu_key.set_latency_threshold(prev)
     exp_msg = np.array([fs[i](int(m)) & 15 for m, i in zip(msgs, idx)], dtype=np.uint64)
     for name, got in outs.items():
         ph = tfhe.phase_batch(client_key.big, got)
@@ -175,9 +194,9 @@ def test_latency_and_throughput_variants_agree(client_key, gpu_key):
         assert np.abs(err).max() < PBS_ERR_MAX and err.std() < PBS_ERR_STD_MAX, name
     # the mask words are not comparable (a last-bit difference of an f64 rounding changes later digits, i.e. the
     # noise realisation), the phases are: both are encryptions of the same value with noise of the same size
-    ph_l = tfhe.phase_batch(client_key.big, outs["latency"])
     ph_t = tfhe.phase_batch(client_key.big, outs["throughput"])
-    assert np.abs(tfhe.torus_err(ph_l, ph_t)).max() < 2 * PBS_ERR_MAX
+    for name in ("cluster", "latency"):
+        assert np.abs(tfhe.torus_err(tfhe.phase_batch(client_key.big, outs[name]), ph_t)).max() < 2 * PBS_ERR_MAX, name
 
 
 def test_empty_batches(gpu_key):

@@ -11,7 +11,9 @@ sk = fb.ServerKey(ksk, bsk)
 lut = fb.make_lut(lambda x: (x + 1) % 16)
 base = ck.encrypt_blocks(np.arange(64) % 16, seed=3)
 sk.timing(True)
-sk.set_latency_threshold(1 << 30)
+variant = os.environ.get("PROBE_VARIANT", "latency")
+sk.set_cluster_threshold((1 << 30) if variant == "cluster" else 0)
+sk.set_latency_threshold((1 << 30) if variant == "latency" else 0)
 for B in [int(a) for a in sys.argv[1:]] or [148]:
     cts = np.ascontiguousarray(np.tile(base, ((B + 63) // 64, 1))[:B])
     idx = np.zeros(B, dtype=np.uint32)
@@ -21,6 +23,6 @@ for B in [int(a) for a in sys.argv[1:]] or [148]:
     for _ in range(5):
         sk.pbs(cts, lut[None], idx)
     st = sk.kernel_stats(reset=True)
-    print("B=%d br_ms=%.4f ks_ms=%.4f ok=%s env=%s" % (B, st["br_ms"] / 5, st["ks_ms"] / 5, ok,
+    print(variant, "B=%d br_ms=%.4f ks_ms=%.4f ok=%s env=%s" % (B, st["br_ms"] / 5, st["ks_ms"] / 5, ok,
           {k: v for k, v in os.environ.items() if k.startswith("FB_")}), flush=True)
 sk.close()
