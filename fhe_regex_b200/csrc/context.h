@@ -31,7 +31,8 @@ struct fb_ctx {
   fb::c2* d_tabs = nullptr;
   fb::c2* d_wtab = nullptr;    // table of the latency blind rotation (inside the d_tabs allocation)
   fb::c2* d_dtab = nullptr;    // table of the cluster blind rotation (inside the d_tabs allocation)
-  int duo_max = 0;             // batches up to this many PBS take the cluster kernel (pairs the device runs at once; env FB_DUO_MAX)
+  int duo_max = 0;             // batches up to this many PBS take the cluster kernel (off by default; env FB_DUO_MAX)
+  int duo_pairs = 0;           // CTA pairs the device runs at once (cudaOccupancyMaxActiveClusters)
   int quantum = 592;           // SM count x PBS per CTA of the throughput blind rotation
   int wide_max = 296;          // batches up to this many PBS take the latency kernel (env FB_WIDE_MAX; 0 = never)
   bool have_key = false;

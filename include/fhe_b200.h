@@ -143,8 +143,8 @@ int fb_measure_fp64_peak(fb_ctx* ctx, int reps, double* tflops);
  * larger ones the throughput variant (up to 4 PBS per CTA).  Default 296 (two waves of 148 SMs), 0 = never.
  * Returns the previous value (or a negative error code).  Both variants compute the same function. */
 int fb_set_latency_threshold(fb_ctx* ctx, int max_count);
-/* Batches of up to max_count PBS run the cluster variant (one PBS per pair of SMs, br_duo.cu).  Default: the number
- * of CTA pairs the device runs at once (74 on a 148-SM B200), 0 = never.  Returns the previous value. */
+/* Batches of up to max_count PBS run the cluster variant (one PBS per pair of SMs, br_duo.cu).  Default 0 = never:
+ * measured on B200 it is no faster than the one-PBS-per-CTA kernel.  Returns the previous value. */
 int fb_set_cluster_threshold(fb_ctx* ctx, int max_count);
 /* PBS batch sizes that fill the GPU evenly are multiples of this (SM count x samples per CTA) */
 int fb_pbs_batch_quantum(fb_ctx* ctx);
