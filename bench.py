@@ -148,7 +148,7 @@ def run_reference(args, rank: int):
         return
     from oracle import tfhe
     threads = tfhe.max_threads()
-    per_step = max(threads * 4, 32)
+    per_step = max(threads * 32, 64)   # ~1-2 s of host work per step
     ock = tfhe.ClientKey.load(CK_PATH)
     osk = tfhe.keygen_server(ock, seed=0)
     osk.fbsk
@@ -391,9 +391,9 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             from oracle import tfhe
             threads = tfhe.max_threads()
-            n = args.cpu_samples or max(64, threads * 16)
+            n = args.cpu_samples or max(256, threads * 256)   # ~10-15 s on the box's host cores
             v, dt = cpu_pbs_rate(n, threads)
-            v1, dt1 = cpu_pbs_rate(8, 1)
+            v1, dt1 = cpu_pbs_rate(64, 1)                     # ~3 s: the reference itself is single-threaded (execution.rs:76-190)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": "%d PBS, OpenMP over the batch, %.1f s; single thread: %.1f PBS/s (%.1f ms/PBS)" % (n, dt, v1, 1e3 / v1),
                                     "single_thread_value": v1}
