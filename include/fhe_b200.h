@@ -103,8 +103,10 @@ typedef struct fb_match_stats {
  * (mod.rs:17) returns the same 0/1 as the reference.  stats may be NULL. */
 int fb_has_match(fb_ctx* ctx, const uint64_t* h_content, size_t n_chars, const char* pattern, uint64_t* h_out,
                  fb_match_stats* stats);
-/* rank's share of the variants (start offsets i with i % world == rank); partial results are OR-folded
- * with fb_or_fold after an all-gather */
+/* rank's share of the match: the rank-th of `world` contiguous slices of the final OR's operands after global
+ * absorption (reference-shaped plan, FB_PLAN_NO_ABSORB: the variants of start offsets i % world == rank).  The OR
+ * of all ranks' results is the match result: all-gather them and fold with fb_or_fold.  stats
+ * carries the reference's counters of the whole match and pbs / levels of this rank's plan. */
 int fb_has_match_shard(fb_ctx* ctx, const uint64_t* h_content, size_t n_chars, const char* pattern, int rank, int world,
                        uint64_t* h_out, fb_match_stats* stats);
 /* OR of n single-block booleans h_in[n][2049] -> h_out[4][2049] radix (the final fold, engine.rs:30-33) */
