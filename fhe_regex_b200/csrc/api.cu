@@ -87,6 +87,9 @@ extern "C" void fb_ctx_destroy(fb_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (auto& p : ctx->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (auto& p : ctx->pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+  for (auto& e : ctx->pipe_events) cudaEventDestroy(e);
+  if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
+  if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
   cudaFree(ctx->d_kb);
   cudaFree(ctx->d_fbsk);
   cudaFree(ctx->d_tabs);
@@ -340,11 +343,51 @@ extern "C" int fb_pbs_batch(fb_ctx* ctx, const uint64_t* h_in, const uint64_t* h
   if ((rc = upload_luts(ctx, h_luts, n_luts, h_lut_idx, count))) return rc;
   if ((rc = fb_reserve(ctx, ctx->in, count * FB_LWE_BIG_WORDS * 8))) return rc;
   if ((rc = fb_reserve(ctx, ctx->out, count * FB_LWE_BIG_WORDS * 8))) return rc;
-  FB_CUDA(ctx, cudaMemcpyAsync(ctx->in.p, h_in, count * FB_LWE_BIG_WORDS * 8, cudaMemcpyHostToDevice, ctx->stream));
-  if ((rc = fb_pbs_batch_dev(ctx, (const uint64_t*)ctx->in.p, (const uint64_t*)ctx->luts.p, (const uint32_t*)ctx->lut_idx.p,
-                             count, (uint64_t*)ctx->out.p)))
-    return rc;
-  FB_CUDA(ctx, cudaMemcpyAsync(h_out, ctx->out.p, count * FB_LWE_BIG_WORDS * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  uint64_t* d_in = (uint64_t*)ctx->in.p;
+  uint64_t* d_out = (uint64_t*)ctx->out.p;
+  const uint32_t* d_idx = (const uint32_t*)ctx->lut_idx.p;
+  // Large batches are pipelined in chunks of whole throughput waves: the upload of chunk k+1 and the download of
+  // chunk k-1 run on their own streams (two DMA engines) under the bootstraps of chunk k, so only the first
+  // upload and the last download are exposed.
+  const size_t chunk = (size_t)ctx->quantum * 4;
+  const size_t n_chunks = (count + chunk - 1) / chunk;
+  if (n_chunks < 2) {
+    FB_CUDA(ctx, cudaMemcpyAsync(d_in, h_in, count * FB_LWE_BIG_WORDS * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = fb_pbs_batch_dev(ctx, d_in, (const uint64_t*)ctx->luts.p, d_idx, count, d_out))) return rc;
+    FB_CUDA(ctx, cudaMemcpyAsync(h_out, d_out, count * FB_LWE_BIG_WORDS * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FB_OK;
+  }
+  if (!ctx->h2d_stream) FB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
+  if (!ctx->d2h_stream) FB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+  while (ctx->pipe_events.size() < 2 * n_chunks + 1) {
+    cudaEvent_t e;
+    FB_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->pipe_events.push_back(e);
+  }
+  // the LUT upload (and whatever the caller queued before) precedes the first bootstrap; the copy streams must not
+  // overwrite buffers an earlier call on the context stream may still use
+  cudaEvent_t start = ctx->pipe_events[2 * n_chunks];
+  FB_CUDA(ctx, cudaEventRecord(start, ctx->stream));
+  FB_CUDA(ctx, cudaStreamWaitEvent(ctx->h2d_stream, start, 0));
+  FB_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h_stream, start, 0));
+  for (size_t k = 0; k < n_chunks; k++) {
+    const size_t off = k * chunk, n = std::min(chunk, count - off);
+    FB_CUDA(ctx, cudaMemcpyAsync(d_in + off * FB_LWE_BIG_WORDS, h_in + off * FB_LWE_BIG_WORDS, n * FB_LWE_BIG_WORDS * 8,
+                                 cudaMemcpyHostToDevice, ctx->h2d_stream));
+    FB_CUDA(ctx, cudaEventRecord(ctx->pipe_events[2 * k], ctx->h2d_stream));
+  }
+  for (size_t k = 0; k < n_chunks; k++) {
+    const size_t off = k * chunk, n = std::min(chunk, count - off);
+    FB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->pipe_events[2 * k], 0));
+    if ((rc = fb_pbs_batch_dev(ctx, d_in + off * FB_LWE_BIG_WORDS, (const uint64_t*)ctx->luts.p, d_idx + off, n, d_out + off * FB_LWE_BIG_WORDS)))
+      return rc;
+    FB_CUDA(ctx, cudaEventRecord(ctx->pipe_events[2 * k + 1], ctx->stream));
+    FB_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h_stream, ctx->pipe_events[2 * k + 1], 0));
+    FB_CUDA(ctx, cudaMemcpyAsync(h_out + off * FB_LWE_BIG_WORDS, d_out + off * FB_LWE_BIG_WORDS, n * FB_LWE_BIG_WORDS * 8,
+                                 cudaMemcpyDeviceToHost, ctx->d2h_stream));
+  }
+  FB_CUDA(ctx, cudaStreamSynchronize(ctx->d2h_stream));
   FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return FB_OK;
 }

@@ -82,13 +82,18 @@ blind_rotate_wide_kernel(const c2* __restrict__ fbsk, const uint64_t* __restrict
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     if (n > 0) issue_ggsw(steps[0], 0);
   }
-  // accumulator init: (0, lut * X^{-b}), top words
+  // accumulator init: (0, lut * X^{-b}), top words; thread (P, t) owns coefficients t + 128m and t + 128m + 1024 of polynomial P
+  uint32_t own[16];
   {
     const uint64_t* lut = luts + (size_t)lut_idx[sample] * kN;
     const uint32_t rot = (4096u - (uint32_t)at[kLweN]) & 4095u;
-    for (int j = tid; j < kN; j += wide::kThreads) {
-      acc[j] = 0u;
-      acc[kN + j] = (uint32_t)(rot_read(lut, (uint32_t)j, rot) >> 32);
+#pragma unroll
+    for (int m = 0; m < 8; m++) {
+      const uint32_t j = (uint32_t)t + 128u * m;
+      own[2 * m] = (P == 0) ? 0u : (uint32_t)(rot_read(lut, j, rot) >> 32);
+      own[2 * m + 1] = (P == 0) ? 0u : (uint32_t)(rot_read(lut, j + 1024u, rot) >> 32);
+      acc[P * kN + j] = own[2 * m];
+      acc[P * kN + j + 1024u] = own[2 * m + 1];
     }
   }
   __syncthreads();
@@ -106,7 +111,7 @@ blind_rotate_wide_kernel(const c2* __restrict__ fbsk, const uint64_t* __restrict
     if (tid == 0 && n + 1 < n_steps) issue_ggsw(steps[n + 1], (n + 1) & 1);
     // The two polynomials only meet in the Fourier MAC: everywhere else a half (128 threads) synchronises on its
     // own named barrier, so one half's transform arithmetic overlaps the other half's shared-memory traffic.
-    wide::fwd_stage1(accp, a, t, tw, bufA_p);
+    wide::fwd_stage1(accp, own, a, t, tw, bufA_p);
     half_sync(P);
     wide::fwd_stage2(bufA_p, bufB_p, t, tw);
     half_sync(P);
@@ -125,7 +130,7 @@ blind_rotate_wide_kernel(const c2* __restrict__ fbsk, const uint64_t* __restrict
     half_sync(P);
     wide::inv_stage3(bufA_p, bufB_p, t);
     half_sync(P);
-    wide::phaseC_accumulate(bufB_p, t, accp);
+    wide::phaseC_accumulate(bufB_p, t, own, accp);
     half_sync(P);
   }
   __syncthreads();

@@ -104,14 +104,16 @@ FB_HD void fwd_stage1_core(c2 (&x)[8], int t, const Tw& tw, c2* out) {
   for (int k = 0; k < 8; k++) out[swz(8 * t + k)] = cmul(x[k], tw.w1f[k]);
 }
 
-// phase A + forward stage 1: digits of (acc X^a - acc) for coefficients j = t + 128 m and j + 1024
-FB_HD void fwd_stage1(const uint32_t* accp, uint32_t a, int t, const Tw& tw, c2* out) {
+// phase A + forward stage 1: digits of (acc X^a - acc) for coefficients j = t + 128 m and j + 1024.
+// own[2m], own[2m+1]: this thread's accumulator words of those coefficients (registers; the thread that rounds
+// coefficient j in phase C is the one that decomposes it here); accp: the shared copy, for the rotated reads
+FB_HD void fwd_stage1(const uint32_t* accp, const uint32_t (&own)[16], uint32_t a, int t, const Tw& tw, c2* out) {
   c2 x[8];
 #pragma unroll
   for (int m = 0; m < 8; m++) {
     const uint32_t j = (uint32_t)t + 128u * m;
-    x[m].x = pbs_digit32(rot_read32(accp, j, a) - accp[j]);
-    x[m].y = pbs_digit32(rot_read32(accp, j + 1024u, a) - accp[j + 1024u]);
+    x[m].x = pbs_digit32(rot_read32(accp, j, a) - own[2 * m]);
+    x[m].y = pbs_digit32(rot_read32(accp, j + 1024u, a) - own[2 * m + 1]);
   }
   fwd_stage1_core(x, t, tw, out);
 }
@@ -251,14 +253,16 @@ FB_HD void inv_stage4(const c2* in, int t, uint32_t (&inc_re)[8], uint32_t (&inc
   }
 }
 
-FB_HD void phaseC_accumulate(const c2* in, int t, uint32_t* accp) {
+FB_HD void phaseC_accumulate(const c2* in, int t, uint32_t (&own)[16], uint32_t* accp) {
   uint32_t ire[8], iim[8];
   inv_stage4(in, t, ire, iim);
 #pragma unroll
   for (int m = 0; m < 8; m++) {
     const int j = t + 128 * m;
-    accp[j] += ire[m];
-    accp[j + 1024] += iim[m];
+    own[2 * m] += ire[m];
+    own[2 * m + 1] += iim[m];
+    accp[j] = own[2 * m];
+    accp[j + 1024] = own[2 * m + 1];
   }
 }
 

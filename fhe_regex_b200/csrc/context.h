@@ -24,6 +24,8 @@ struct fb_event_pair {
 struct fb_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;   // fb_pbs_batch: copies of neighbouring chunks under the bootstraps
+  std::vector<cudaEvent_t> pipe_events;
   std::string err;
   // keys
   uint8_t* d_kb = nullptr;     // byte planes of the KSK for the tensor-core keyswitch

@@ -14,7 +14,8 @@ namespace {
 struct Cta {
   std::vector<c2> tab;          // [kTabC2]
   std::vector<c2> bufA, bufB;   // [2][1024]
-  std::vector<uint32_t> acc;    // [2][2048]
+  std::vector<uint32_t> acc;    // [2][2048] shared copy
+  uint32_t own[256][16];        // registers: thread (P, t) owns coefficients t + 128m (+1024) of polynomial P
   Tw tw[256];
   Cta() : tab(kTabC2), bufA(2 * kHalfN), bufB(2 * kHalfN), acc(2 * kN) {
     make_wide_table(tab.data());
@@ -80,7 +81,8 @@ extern "C" void emu_wide_negacyclic_mul(const int64_t* a_int, const uint64_t* b_
   }
   inverse_tail(c);
   std::fill(c.acc.begin(), c.acc.end(), 0u);
-  for (int tid = 0; tid < 256; tid++) phaseC_accumulate(c.bufB.data() + (tid >> 7) * kHalfN, tid & 127, c.acc.data() + (tid >> 7) * kN);
+  memset(c.own, 0, sizeof c.own);
+  for (int tid = 0; tid < 256; tid++) phaseC_accumulate(c.bufB.data() + (tid >> 7) * kHalfN, tid & 127, c.own[tid], c.acc.data() + (tid >> 7) * kN);
   for (int j = 0; j < kN; j++) out[j] = (uint64_t)c.acc[j] << 32;
   delete &c;
 }
@@ -94,17 +96,22 @@ extern "C" void emu_wide_blind_rotate(const c2* fbsk, const uint64_t* small, con
     c.acc[j] = 0;
     c.acc[kN + j] = (uint32_t)(rot_read(lut, j, rot) >> 32);
   }
+  for (int tid = 0; tid < 256; tid++)
+    for (int m = 0; m < 8; m++) {
+      c.own[tid][2 * m] = c.acc[(tid >> 7) * kN + (tid & 127) + 128 * m];
+      c.own[tid][2 * m + 1] = c.acc[(tid >> 7) * kN + (tid & 127) + 128 * m + 1024];
+    }
   const int steps = max_steps < 0 ? kLweN : max_steps;
   for (int i = 0; i < steps; i++) {
     const uint32_t a = modswitch(small[i]) & 4095u;
     if (small[i] == 0 || a == 0) continue;
     const c2* ggsw = fbsk + (size_t)i * 4 * kHalfN;
-    for (int tid = 0; tid < 256; tid++) fwd_stage1(c.acc.data() + (tid >> 7) * kN, a, tid & 127, c.tw[tid], c.bufA.data() + (tid >> 7) * kHalfN);
+    for (int tid = 0; tid < 256; tid++) fwd_stage1(c.acc.data() + (tid >> 7) * kN, c.own[tid], a, tid & 127, c.tw[tid], c.bufA.data() + (tid >> 7) * kHalfN);
     forward_tail(c);
     for (int tid = 0; tid < 256; tid++)
       mac_inv_stage1(c.bufA.data(), c.bufA.data() + kHalfN, ggsw, tid >> 7, tid & 127, c.tw[tid], c.bufB.data() + (tid >> 7) * kHalfN);
     inverse_tail(c);
-    for (int tid = 0; tid < 256; tid++) phaseC_accumulate(c.bufB.data() + (tid >> 7) * kHalfN, tid & 127, c.acc.data() + (tid >> 7) * kN);
+    for (int tid = 0; tid < 256; tid++) phaseC_accumulate(c.bufB.data() + (tid >> 7) * kHalfN, tid & 127, c.own[tid], c.acc.data() + (tid >> 7) * kN);
   }
   for (int j = 0; j < 2 * kN; j++) acc_out[j] = (uint64_t)c.acc[j] << 32;
   delete &c;
