@@ -199,6 +199,29 @@ def test_blind_rotation_variants_agree(client_key, gpu_key):
         assert np.abs(tfhe.torus_err(tfhe.phase_batch(client_key.big, outs[name]), ph_t)).max() < 2 * PBS_ERR_MAX, name
 
 
+def test_pbs_batch_pipelined_chunks(fck, gpu_key):
+    """fb_pbs_batch splits batches beyond 8 throughput quanta into chunks whose copies overlap the bootstraps:
+    every chunk, both sides of every chunk boundary and the ragged tail must come back right"""
+    q = gpu_key.pbs_quantum()
+    count = 2 * 8 * q + 8 * q // 2 + 37                     # three chunks, the last one ragged
+    base_msgs = (np.arange(128) * 5 + 1) % 16
+    base = fck.encrypt_blocks(base_msgs, seed=91)
+    cts = np.ascontiguousarray(np.tile(base, ((count + 127) // 128, 1))[:count])
+    msgs = np.tile(base_msgs, (count + 127) // 128)[:count]
+    fs = [lambda x: (x + 9) % 16, lambda x: int(x < 4), lambda x: (3 * x) % 16]
+    luts = np.stack([fb.make_lut(f) for f in fs])
+    idx = (np.arange(count) % 3).astype(np.uint32)
+    out = gpu_key.pbs(cts, luts, idx)
+    third = ((count + 2) // 3 + q - 1) // q * q
+    chunk = max(8 * q, third)
+    pick = {0, 1, count - 1, count - 2, count // 2}
+    for b in range(chunk, count, chunk):
+        pick |= {b - 1, b, b + 1}
+    pick |= set(range(0, count, 997))
+    for i in sorted(pick):
+        assert fck.decrypt_block(out[i]) == fs[int(idx[i])](int(msgs[i])) & 15, (count, i)
+
+
 def test_empty_batches(gpu_key):
     assert gpu_key.keyswitch(np.zeros((0, tfhe.BIG), dtype=np.uint64)).shape == (0, tfhe.SMALL)
     lut = tfhe.make_lut(lambda x: x)
