@@ -140,6 +140,23 @@ def test_lowering_matches_oracle_random():
         assert int(any(parts)) == exp, (pat, content, parts)
 
 
+def test_long_content_absorbed_and_sharded_plans_match_oracle():
+    """value-level absorption and the contiguous root slices at the sizes the bench uses"""
+    rnd = random.Random(19)
+    for pat, n in [("/a+b?c/", 64), ("/a+b?c/", 150), ("/ab{2,4}c/", 64), (r"/[a-d][^x-z]\./", 64), ("/x[ab]+y/i", 80), ("/aaaa+/", 90)]:
+        for alphabet in ("abcx", "ab", "xyAB."):
+            content = "".join(rnd.choice(alphabet) for _ in range(n))
+            exp = rp.has_match(content, pat)
+            assert fb.plan_eval_plain(pat, content) == exp, (pat, content)
+            for world in (2, 5, 8):
+                parts = [fb.plan_eval_plain(pat, content, r, world) for r in range(world)]
+                assert int(any(parts)) == exp, (pat, content, world, parts)
+    # the slices partition the work: per-rank leaf levels shrink with the world size
+    w1 = fb.plan_level_widths("/a+b?c/", 256)
+    w8 = [fb.plan_level_widths("/a+b?c/", 256, r, 8) for r in range(8)]
+    assert all(w[0] <= w1[0] // 8 + 16 for w in w8), (w1, w8)
+
+
 def test_lowering_config_rows():
     rnd = random.Random(3)
     c64 = "".join(rnd.choice("abcx") for _ in range(64))
