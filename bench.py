@@ -330,7 +330,8 @@ def main():
                                        "hbm_peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * BIG * 8 + luts_np.nbytes + idx_np.nbytes, "d2h_bytes_per_step": B * BIG * 8,
                     "ms_per_step": e2e_ms / args.steps, "api": "fb_pbs_batch (host buffers, pinned)"},
-            "gpu_launches": int(kst["ks_launches"] + kst["br_launches"] + kst["lin_launches"]),
+            # kernels of this repository launched inside the timed region: per step ks_decompose + ks_gemm + blind_rotate
+            "gpu_launches": int(2 * kst["ks_launches"] + kst["br_launches"] + kst["lin_launches"]),
             "clocks": clocks,
         }
 
