@@ -753,43 +753,51 @@ struct Lowering {
     if (cached != pre_absorbed.end()) return cached->second;
     const auto t_begin = std::chrono::steady_clock::now();
     const size_t nv = ex.vals.items.size();
-    std::vector<std::vector<int32_t>> sets(ops.size());
+    // sorted conjunct set of every AND value under the operands, bottom-up and memoised: the operands of a lazily
+    // enumerated match share their prefixes (hash-consed values), so a set is one merge of its children's sets
+    std::vector<std::vector<int32_t>> memo(nv);
+    std::vector<char> state(nv, 0);                  // 0 = not computed, 1 = set ready, 2 = contains a false conjunct
+    auto conj = [&](int32_t root) {
+      std::vector<int32_t> stack{root};
+      while (!stack.empty()) {
+        const int32_t x = stack.back();
+        if (state[x]) { stack.pop_back(); continue; }
+        const Triple tx = ex.vals.items[x];
+        if (tx.t == V_CONST) { state[x] = (tx.a & 1) ? 1 : 2; stack.pop_back(); continue; }   // true: empty set (neutral)
+        if (tx.t != V_AND) { memo[x].assign(1, x); state[x] = 1; stack.pop_back(); continue; }
+        if (!state[tx.a]) { stack.push_back(tx.a); continue; }
+        if (!state[tx.b]) { stack.push_back(tx.b); continue; }
+        if (state[tx.a] == 2 || state[tx.b] == 2) state[x] = 2;
+        else {
+          const auto &A = memo[tx.a], &B = memo[tx.b];
+          memo[x].resize(A.size() + B.size());
+          memo[x].erase(std::set_union(A.begin(), A.end(), B.begin(), B.end(), memo[x].begin()), memo[x].end());
+          state[x] = 1;
+        }
+        stack.pop_back();
+      }
+    };
+    std::vector<const std::vector<int32_t>*> setp(ops.size());
     std::vector<char> dead(ops.size(), 0);
     std::vector<uint32_t> freq(nv, 0);
-    std::vector<int32_t> work;
     for (size_t o = 0; o < ops.size(); o++) {
-      auto& set = sets[o];
-      if (ex.vals.items[ops[o]].t != V_AND) { set.push_back(ops[o]); }
-      else {
-        work.assign(1, ops[o]);
-        while (!work.empty()) {
-          const int32_t x = work.back();
-          work.pop_back();
-          const Triple tx = ex.vals.items[x];
-          if (tx.t == V_AND) { work.push_back(tx.a); work.push_back(tx.b); continue; }
-          if (tx.t == V_CONST) {
-            if (tx.a & 1) continue;          // neutral conjunct
-            dead[o] = 1;                     // a false conjunct: the operand is false, neutral in the OR
-            break;
-          }
-          set.push_back(x);
-        }
-        std::sort(set.begin(), set.end());
-        set.erase(std::unique(set.begin(), set.end()), set.end());
-      }
-      if (!dead[o]) for (int32_t x : set) freq[x]++;
+      conj(ops[o]);
+      dead[o] = state[ops[o]] == 2;                  // a false conjunct: the operand is false, neutral in the OR
+      setp[o] = &memo[ops[o]];
+      if (!dead[o]) for (int32_t x : *setp[o]) freq[x]++;
     }
+    auto sets = [&](size_t o) -> const std::vector<int32_t>& { return *setp[o]; };
     std::vector<uint32_t> order;
     for (size_t o = 0; o < ops.size(); o++) if (!dead[o]) order.push_back((uint32_t)o);
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return sets[a].size() < sets[b].size(); });
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return sets(a).size() < sets(b).size(); });
     std::vector<std::vector<uint32_t>> by_rare(nv);
     std::vector<char> keep(ops.size(), 0);
     for (uint32_t o : order) {
-      const auto& B = sets[o];
-      bool implied = B.empty() ? false : false;
+      const auto& B = sets(o);
+      bool implied = false;
       for (size_t bi = 0; bi < B.size() && !implied; bi++)
         for (uint32_t a : by_rare[B[bi]]) {
-          const auto& A = sets[a];
+          const auto& A = sets(a);
           if (A.size() <= B.size() && std::includes(B.begin(), B.end(), A.begin(), A.end())) { implied = true; break; }
         }
       if (implied) { absorbed++; continue; }
