@@ -380,7 +380,26 @@ def main():
                                 "levels": st["levels"], "level_widths_rank0": fb.plan_level_widths(pattern, len(content), rank, world),
                                 "ref_ct_ops_rank0": st["ct_ops"], "result": res})
         os.environ.pop("FB_PLAN_NO_ABSORB", None)
+        # many contents against one pattern in shared launches (fb_has_match_many): the levels are wide enough for
+        # the throughput kernel, a match costs its PBS at the throughput rate instead of one latency per level
+        many = []
+        if world == 1:
+            for n_chars, m, pattern in ((64, 64, "/a+b?c/"), (256, 16, "/a+b?c/")):
+                rng2 = np.random.default_rng(11)
+                texts = ["".join(rng2.choice(list("abcx"), size=n_chars)) for _ in range(m)]
+                base = [fb.encrypt_str(ck, t_, seed=20 + i) for i, t_ in enumerate(texts[:4])]   # 4 distinct encryptions, cycled
+                texts = [texts[i % 4] for i in range(m)]
+                cts = np.stack([base[i % 4] for i in range(m)])
+                fb.has_match_many(sk, cts, pattern)
+                tm = time.perf_counter()
+                outs, st = fb.has_match_many(sk, cts, pattern, return_stats=True)
+                wall = (time.perf_counter() - tm) * 1e3
+                got = [ck.decrypt(o) for o in outs]
+                assert got == [rp.has_match(t_, pattern) for t_ in texts], (pattern, got)
+                many.append({"pattern": pattern, "n_chars": n_chars, "contents": m, "ms_total": wall, "ms_per_match": wall / m,
+                             "gpu_ms_total": st["gpu_ms"], "pbs_per_match": st["pbs"], "matches_per_s": m / (wall * 1e-3)})
         if rank == 0:
+            line["match_many"] = many
             line["match"] = matches
             line["ms_per_match_64"] = matches[0]["ms"]
             line["ms_per_match_256"] = matches[3]["ms"]

@@ -82,6 +82,7 @@ def lib():
     L.fb_pbs_batch_dev.argtypes = [vp, vp, vp, vp, sz, vp]
     L.fb_has_match.argtypes = [vp, vp, sz, C.c_char_p, vp, C.POINTER(MatchStats)]
     L.fb_has_match_shard.argtypes = [vp, vp, sz, C.c_char_p, C.c_int, C.c_int, vp, C.POINTER(MatchStats)]
+    L.fb_has_match_many.argtypes = [vp, vp, sz, sz, C.c_char_p, vp, C.POINTER(MatchStats)]
     L.fb_or_fold.argtypes = [vp, vp, sz, vp]
     L.fb_parse_debug.argtypes = [C.c_char_p, C.c_char_p, sz]
     L.fb_plan_stats.argtypes = [C.c_char_p, sz, C.POINTER(MatchStats)]
@@ -367,5 +368,21 @@ def has_match(server_key: ServerKey, content: np.ndarray, pattern: str, return_s
     out = np.empty((4, BIG), dtype=np.uint64)
     st = MatchStats()
     rc = lib().fb_has_match_shard(server_key._h, _p(content) if n else None, n, pattern.encode("latin-1"), rank, world, _p(out), C.byref(st))
+    server_key._check(rc)
+    return (out, st.as_dict()) if return_stats else out
+
+
+def has_match_many(server_key: ServerKey, contents: np.ndarray, pattern: str, return_stats: bool = False):
+    """The same match for many contents of one length against one pattern, level by level in shared launches.
+
+    contents: [m, n, 4, 2049] u64 (m stacked encrypt_str results).  Returns [m, 4, 2049]: one radix ciphertext per
+    content, each decrypting to what has_match gives for that content alone."""
+    contents = np.ascontiguousarray(contents, dtype=np.uint64)
+    if contents.ndim != 4:
+        raise ValueError("contents must be [m, n_chars, 4, 2049]")
+    m, n = contents.shape[0], contents.shape[1]
+    out = np.empty((m, 4, BIG), dtype=np.uint64)
+    st = MatchStats()
+    rc = lib().fb_has_match_many(server_key._h, _p(contents) if m * n else None, m, n, pattern.encode("latin-1"), _p(out) if m else None, C.byref(st))
     server_key._check(rc)
     return (out, st.as_dict()) if return_stats else out

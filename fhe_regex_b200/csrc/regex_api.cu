@@ -23,23 +23,39 @@ struct DevPlan {
   std::vector<int64_t> i64;
   std::vector<uint64_t> u64;
   std::vector<uint32_t> u32;
-  struct Off { size_t lin_out, lin_off, lin_rows, lin_coef, lin_const, in_rows, lut_idx; int n_lin, n_pbs; int32_t out_base; };
+  struct Off { size_t lin_out, lin_off, lin_rows, lin_coef, lin_const, in_rows, out_rows, lut_idx; int n_lin, n_pbs; int32_t out_base; };
   std::vector<Off> levels;
 };
 
-void flatten_plan(const Plan& plan, DevPlan& d) {
+// m instances of one plan (m contents against one pattern): instance k lives in arena rows [k * n_rows, (k+1) * n_rows),
+// every level's arrays are the instances' arrays back to back, so a level is still one lincomb + one keyswitch +
+// one blind-rotation launch, m times as wide
+void flatten_plan(const Plan& plan, DevPlan& d, size_t m) {
+  const int32_t R = plan.n_rows;
   for (auto& l : plan.levels) {
     DevPlan::Off o;
-    o.n_lin = (int)l.lin_out_rows.size();
-    o.n_pbs = (int)l.in_rows.size();
+    const size_t nl = l.lin_out_rows.size(), np = l.in_rows.size(), nt = l.lin_term_rows.size();
+    o.n_lin = (int)(nl * m);
+    o.n_pbs = (int)(np * m);
     o.out_base = l.out_row_base;
-    o.lin_out = d.i32.size(); d.i32.insert(d.i32.end(), l.lin_out_rows.begin(), l.lin_out_rows.end());
-    o.lin_off = d.i32.size(); d.i32.insert(d.i32.end(), l.lin_term_off.begin(), l.lin_term_off.end());
-    o.lin_rows = d.i32.size(); d.i32.insert(d.i32.end(), l.lin_term_rows.begin(), l.lin_term_rows.end());
-    o.in_rows = d.i32.size(); d.i32.insert(d.i32.end(), l.in_rows.begin(), l.in_rows.end());
-    o.lin_coef = d.i64.size(); d.i64.insert(d.i64.end(), l.lin_coef.begin(), l.lin_coef.end());
-    o.lin_const = d.u64.size(); d.u64.insert(d.u64.end(), l.lin_const.begin(), l.lin_const.end());
-    o.lut_idx = d.u32.size(); d.u32.insert(d.u32.end(), l.lut_idx.begin(), l.lut_idx.end());
+    o.lin_out = d.i32.size();
+    for (size_t k = 0; k < m; k++) for (int32_t r : l.lin_out_rows) d.i32.push_back(r + (int32_t)k * R);
+    o.lin_off = d.i32.size();
+    for (size_t k = 0; k < m; k++) for (size_t j = 0; j < nl; j++) d.i32.push_back(l.lin_term_off[j] + (int32_t)(k * nt));
+    d.i32.push_back((int32_t)(m * nt));
+    o.lin_rows = d.i32.size();
+    for (size_t k = 0; k < m; k++) for (int32_t r : l.lin_term_rows) d.i32.push_back(r + (int32_t)k * R);
+    o.in_rows = d.i32.size();
+    for (size_t k = 0; k < m; k++) for (int32_t r : l.in_rows) d.i32.push_back(r + (int32_t)k * R);
+    o.out_rows = d.i32.size();
+    if (m > 1)
+      for (size_t k = 0; k < m; k++) for (size_t j = 0; j < np; j++) d.i32.push_back(l.out_row_base + (int32_t)j + (int32_t)k * R);
+    o.lin_coef = d.i64.size();
+    for (size_t k = 0; k < m; k++) d.i64.insert(d.i64.end(), l.lin_coef.begin(), l.lin_coef.end());
+    o.lin_const = d.u64.size();
+    for (size_t k = 0; k < m; k++) d.u64.insert(d.u64.end(), l.lin_const.begin(), l.lin_const.end());
+    o.lut_idx = d.u32.size();
+    for (size_t k = 0; k < m; k++) d.u32.insert(d.u32.end(), l.lut_idx.begin(), l.lut_idx.end());
     d.levels.push_back(o);
   }
 }
@@ -59,20 +75,22 @@ void write_trivial_radix(uint64_t* h_out, uint64_t bit) {
   h_out[FB_POLY_SIZE] = bit << 59;
 }
 
-// run a plan; content (n_in_rows x 2049) is uploaded to arena rows [0, n_in_rows)
-int run_plan(fb_ctx* ctx, const Plan& plan, const uint64_t* h_in, size_t n_in_rows, uint64_t* h_out_radix, double* gpu_ms) {
+// run m instances of a plan; instance k's input (n_in_rows x 2049, at h_in + k * n_in_rows rows) is uploaded to the
+// first n_in_rows arena rows of its block, its result radix goes to h_out_radix + k * 4 rows
+int run_plan(fb_ctx* ctx, const Plan& plan, const uint64_t* h_in, size_t n_in_rows, uint64_t* h_out_radix, double* gpu_ms, size_t m = 1) {
   if (plan.result_kind < 2) {
-    write_trivial_radix(h_out_radix, (uint64_t)plan.result_kind);
+    for (size_t k = 0; k < m; k++) write_trivial_radix(h_out_radix + k * 4 * FB_LWE_BIG_WORDS, (uint64_t)plan.result_kind);
     if (gpu_ms) *gpu_ms = 0;
     return FB_OK;
   }
   if (!ctx->have_key) return fb_fail(ctx, FB_ERR_NO_KEY, "server key not loaded");
   FB_CUDA(ctx, cudaSetDevice(ctx->device));
   DevPlan d;
-  flatten_plan(plan, d);
+  flatten_plan(plan, d, m);
   int rc;
-  if ((rc = fb_reserve(ctx, ctx->arena, (size_t)plan.n_rows * FB_LWE_BIG_WORDS * 8))) return rc;
-  if ((rc = fb_reserve(ctx, ctx->small, (size_t)(plan.stats.max_level_width + 1) * FB_LWE_SMALL_WORDS * 8))) return rc;
+  const size_t row_bytes = (size_t)FB_LWE_BIG_WORDS * 8;
+  if ((rc = fb_reserve(ctx, ctx->arena, m * (size_t)plan.n_rows * row_bytes))) return rc;
+  if ((rc = fb_reserve(ctx, ctx->small, (m * (size_t)plan.stats.max_level_width + 1) * FB_LWE_SMALL_WORDS * 8))) return rc;
   if ((rc = fb_reserve(ctx, ctx->plan_i32, (d.i32.size() + 1) * 4))) return rc;
   if ((rc = fb_reserve(ctx, ctx->plan_i64, (d.i64.size() + 1) * 8))) return rc;
   if ((rc = fb_reserve(ctx, ctx->plan_u64, (d.u64.size() + 1) * 8))) return rc;
@@ -95,7 +113,8 @@ int run_plan(fb_ctx* ctx, const Plan& plan, const uint64_t* h_in, size_t n_in_ro
     cudaError_t _e = (call);                                                  \
     if (_e != cudaSuccess) { cleanup(); return fb_cuda_fail(ctx, _e, #call); } \
   } while (0)
-  RP_CUDA(cudaMemcpyAsync(d_arena, h_in, n_in_rows * FB_LWE_BIG_WORDS * 8, cudaMemcpyHostToDevice, st));
+  RP_CUDA(cudaMemcpy2DAsync(d_arena, (size_t)plan.n_rows * row_bytes, h_in, n_in_rows * row_bytes, n_in_rows * row_bytes, m,
+                            cudaMemcpyHostToDevice, st));
   RP_CUDA(cudaMemcpyAsync(d_i32, d.i32.data(), d.i32.size() * 4, cudaMemcpyHostToDevice, st));
   RP_CUDA(cudaMemcpyAsync(d_i64, d.i64.data(), d.i64.size() * 8, cudaMemcpyHostToDevice, st));
   RP_CUDA(cudaMemcpyAsync(d_u64, d.u64.data(), d.u64.size() * 8, cudaMemcpyHostToDevice, st));
@@ -118,13 +137,15 @@ int run_plan(fb_ctx* ctx, const Plan& plan, const uint64_t* h_in, size_t n_in_ro
     if (o.n_pbs > 0) {
       rc = fb_run_keyswitch(ctx, d_arena, d_i32 + o.in_rows, d_small, o.n_pbs);
       if (rc) { cleanup(); return rc; }
-      rc = fb_run_blind_rotate(ctx, d_small, d_luts, d_u32 + o.lut_idx, d_arena + (size_t)o.out_base * FB_LWE_BIG_WORDS, nullptr, o.n_pbs);
+      rc = (m == 1) ? fb_run_blind_rotate(ctx, d_small, d_luts, d_u32 + o.lut_idx, d_arena + (size_t)o.out_base * FB_LWE_BIG_WORDS, nullptr, o.n_pbs)
+                    : fb_run_blind_rotate(ctx, d_small, d_luts, d_u32 + o.lut_idx, d_arena, d_i32 + o.out_rows, o.n_pbs);
       if (rc) { cleanup(); return rc; }
     }
   }
   RP_CUDA(cudaEventRecord(ev1, st));
-  std::memset(h_out_radix, 0, sizeof(uint64_t) * 4 * FB_LWE_BIG_WORDS);
-  RP_CUDA(cudaMemcpyAsync(h_out_radix, d_arena + (size_t)plan.result_row * FB_LWE_BIG_WORDS, FB_LWE_BIG_WORDS * 8, cudaMemcpyDeviceToHost, st));
+  std::memset(h_out_radix, 0, m * 4 * row_bytes);
+  RP_CUDA(cudaMemcpy2DAsync(h_out_radix, 4 * row_bytes, d_arena + (size_t)plan.result_row * FB_LWE_BIG_WORDS, (size_t)plan.n_rows * row_bytes,
+                            row_bytes, m, cudaMemcpyDeviceToHost, st));
   RP_CUDA(cudaStreamSynchronize(st));
   float ms = 0.f;
   RP_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
@@ -182,30 +203,60 @@ extern "C" int fb_plan_eval_plain(const char* pattern, const uint8_t* content, s
   return eval_plan_plain(plan, content, 0, result, err);
 }
 
-extern "C" int fb_has_match_shard(fb_ctx* ctx, const uint64_t* h_content, size_t n_chars, const char* pattern, int rank,
-                                  int world, uint64_t* h_out, fb_match_stats* stats) {
-  if (!ctx || !pattern || !h_out || (!h_content && n_chars)) return fb_fail(ctx, FB_ERR_ARG, "null argument");
+static int cached_plan(fb_ctx* ctx, const char* pattern, size_t n_chars, int rank, int world, std::shared_ptr<const Plan>& plan) {
   const std::string key = std::string(pattern) + '\n' + std::to_string(n_chars) + '/' + std::to_string(rank) + '/' + std::to_string(world) +
                           (std::getenv("FB_PLAN_NO_ABSORB") ? "/ref-shaped" : "/absorbed");
-  std::shared_ptr<const Plan> plan;
   for (size_t i = 0; i < ctx->plan_cache.size(); i++)
     if (ctx->plan_cache[i].first == key) {
       plan = ctx->plan_cache[i].second;
       std::rotate(ctx->plan_cache.begin(), ctx->plan_cache.begin() + i, ctx->plan_cache.begin() + i + 1);
-      break;
+      return FB_OK;
     }
-  if (!plan) {
-    auto fresh = std::make_shared<Plan>();
-    std::string err;
-    int rc = build_plan(pattern, n_chars, rank, world, *fresh, err);
-    if (rc != FB_OK) return fb_fail(ctx, rc, err);
-    plan = fresh;
-    ctx->plan_cache.insert(ctx->plan_cache.begin(), std::make_pair(key, plan));
-    if (ctx->plan_cache.size() > 8) ctx->plan_cache.pop_back();
-  }
-  double ms = 0;
-  int rc = run_plan(ctx, *plan, h_content, 4 * n_chars, h_out, &ms);
+  auto fresh = std::make_shared<Plan>();
+  std::string err;
+  int rc = build_plan(pattern, n_chars, rank, world, *fresh, err);
+  if (rc != FB_OK) return fb_fail(ctx, rc, err);
+  plan = fresh;
+  ctx->plan_cache.insert(ctx->plan_cache.begin(), std::make_pair(key, plan));
+  if (ctx->plan_cache.size() > 8) ctx->plan_cache.pop_back();
+  return FB_OK;
+}
+
+extern "C" int fb_has_match_shard(fb_ctx* ctx, const uint64_t* h_content, size_t n_chars, const char* pattern, int rank,
+                                  int world, uint64_t* h_out, fb_match_stats* stats) {
+  if (!ctx || !pattern || !h_out || (!h_content && n_chars)) return fb_fail(ctx, FB_ERR_ARG, "null argument");
+  std::shared_ptr<const Plan> plan;
+  int rc = cached_plan(ctx, pattern, n_chars, rank, world, plan);
   if (rc != FB_OK) return rc;
+  double ms = 0;
+  rc = run_plan(ctx, *plan, h_content, 4 * n_chars, h_out, &ms);
+  if (rc != FB_OK) return rc;
+  if (stats) {
+    *stats = plan->stats;
+    stats->gpu_ms = ms;
+  }
+  return FB_OK;
+}
+
+extern "C" int fb_has_match_many(fb_ctx* ctx, const uint64_t* h_contents, size_t n_contents, size_t n_chars, const char* pattern,
+                                 uint64_t* h_out, fb_match_stats* stats) {
+  if (!ctx || !pattern || (!h_out && n_contents) || (!h_contents && n_chars && n_contents)) return fb_fail(ctx, FB_ERR_ARG, "null argument");
+  std::shared_ptr<const Plan> plan;
+  int rc = cached_plan(ctx, pattern, n_chars, 0, 1, plan);
+  if (rc != FB_OK) return rc;
+  double ms = 0;
+  if (n_contents > 0) {
+    // bound the arena: instances are processed in groups of at most ~8 GiB of ciphertext rows
+    const size_t per = std::max<size_t>(1, (size_t)plan->n_rows) * FB_LWE_BIG_WORDS * 8;
+    const size_t group = std::max<size_t>(1, std::min<size_t>(n_contents, ((size_t)8 << 30) / per));
+    for (size_t k0 = 0; k0 < n_contents; k0 += group) {
+      const size_t mk = std::min(group, n_contents - k0);
+      double part = 0;
+      rc = run_plan(ctx, *plan, h_contents + k0 * 4 * n_chars * FB_LWE_BIG_WORDS, 4 * n_chars, h_out + k0 * 4 * FB_LWE_BIG_WORDS, &part, mk);
+      if (rc != FB_OK) return rc;
+      ms += part;
+    }
+  }
   if (stats) {
     *stats = plan->stats;
     stats->gpu_ms = ms;

@@ -103,6 +103,13 @@ typedef struct fb_match_stats {
  * (mod.rs:17) returns the same 0/1 as the reference.  stats may be NULL. */
 int fb_has_match(fb_ctx* ctx, const uint64_t* h_content, size_t n_chars, const char* pattern, uint64_t* h_out,
                  fb_match_stats* stats);
+/* The same match for n_contents contents of n_chars characters each against one pattern -- what a server holding many
+ * encrypted documents does with engine.rs:8-42.  h_contents[n_contents][n_chars][4][2049], h_out[n_contents][4][2049].
+ * The instances share one plan and run level by level in the same launches (every PBS batch n_contents times as wide),
+ * so the GPU works at its throughput rate instead of one blind-rotation latency per level and content.
+ * stats: the per-content counters; gpu_ms is the total. */
+int fb_has_match_many(fb_ctx* ctx, const uint64_t* h_contents, size_t n_contents, size_t n_chars, const char* pattern,
+                      uint64_t* h_out, fb_match_stats* stats);
 /* rank's share of the match: the rank-th of `world` contiguous slices of the final OR's operands after global
  * absorption (reference-shaped plan, FB_PLAN_NO_ABSORB: the variants of start offsets i % world == rank).  The OR
  * of all ranks' results is the match result: all-gather them and fold with fb_or_fold.  stats

@@ -281,6 +281,24 @@ def test_has_match_256_char_config5_both_plans(fck, gpu_key, monkeypatch):
     assert fck.decrypt(res) == 1 and st["pbs"] > 60000 and (st["ct_ops"], st["cache_hits"]) == (195583, 11118596)
 
 
+def test_has_match_many_contents_share_the_launches(fck, gpu_key):
+    """m contents against one pattern in shared launches: every result is what has_match gives for that content alone"""
+    cases = [("/ab{2,4}c/", ["xabbcx", "xabcxx", "abbbbc", "cbbbba", "abbbbb", "aabbcc", "xxxxxx"]),
+             ("/a+b?c/", ["aaabcxxxxxxxxxxxxxxx", "xxxxxxxxxxxxxxxxxxac", "bbbbbbbbbbbbbbbbbbbb", "aaaaaaaaaaaaaaaaaaab", "cabcabxxxxxxxxxxxxxx"]),
+             ("/^abc$/", ["abc", "abd", "xbc"])]
+    for pattern, contents in cases:
+        cts = np.stack([fb.encrypt_str(fck, c, seed=40 + i) for i, c in enumerate(contents)])
+        outs, st = fb.has_match_many(gpu_key, cts, pattern, return_stats=True)
+        assert outs.shape == (len(contents), 4, tfhe.BIG)
+        got = [fck.decrypt(o) for o in outs]
+        assert got == [rp.has_match(c, pattern) for c in contents], (pattern, got)
+        assert st["pbs"] == fb.plan_stats(pattern, len(contents[0]))["pbs"]
+    # degenerate shapes: no content at all, a plan that is a constant
+    assert fb.has_match_many(gpu_key, np.zeros((0, 3, 4, tfhe.BIG), dtype=np.uint64), "/abc/").shape == (0, 4, tfhe.BIG)
+    two = np.stack([fb.encrypt_str(fck, "ab"), fb.encrypt_str(fck, "cd")])
+    assert [fck.decrypt(o) for o in fb.has_match_many(gpu_key, two, "/^abc$/")] == [0, 0]
+
+
 def test_sharded_match_and_or_fold(fck, gpu_key):
     content = "xxabbcxxxxaacxxx"
     ct = fb.encrypt_str(fck, content, seed=2)
