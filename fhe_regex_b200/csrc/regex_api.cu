@@ -89,7 +89,9 @@ int run_plan(fb_ctx* ctx, const Plan& plan, const uint64_t* h_in, size_t n_in_ro
   flatten_plan(plan, d, m);
   int rc;
   const size_t row_bytes = (size_t)FB_LWE_BIG_WORDS * 8;
-  if ((rc = fb_reserve(ctx, ctx->arena, m * (size_t)plan.n_rows * row_bytes))) return rc;
+  // at least 1 GiB from the first match on (65 536 ciphertext rows; the device has 180 GB): growing the arena means
+  // a device-wide cudaFree + cudaMalloc in the middle of a serving loop
+  if ((rc = fb_reserve(ctx, ctx->arena, std::max<size_t>(m * (size_t)plan.n_rows * row_bytes, (size_t)1 << 30)))) return rc;
   if ((rc = fb_reserve(ctx, ctx->small, (m * (size_t)plan.stats.max_level_width + 1) * FB_LWE_SMALL_WORDS * 8))) return rc;
   if ((rc = fb_reserve(ctx, ctx->plan_i32, (d.i32.size() + 1) * 4))) return rc;
   if ((rc = fb_reserve(ctx, ctx->plan_i64, (d.i64.size() + 1) * 8))) return rc;
