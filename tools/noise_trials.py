@@ -2,7 +2,7 @@
 """Bootstrap correctness / noise over many trials on the GPU (north-star criterion: no decryption failure
 across >= 10^6 trials, output-noise variance within the parameter set's bound).
 
-    python tools/noise_trials.py [trials] [--json out.json]
+    python tools/noise_trials.py [trials] [--variant throughput|latency|cluster] [--json out.json]
 
 Every trial is a fresh encryption (own mask, own Gaussian noise) of a uniform 4-bit message, bootstrapped
 through a LUT drawn from the has_match table plus identity / affine LUTs.  Outputs are decrypted on the CPU
@@ -19,10 +19,14 @@ sys.path.insert(0, ROOT)
 import fhe_regex_b200 as fb  # noqa: E402
 
 
-def run(trials: int, chunk: int = 28416, seed: int = 2026):
+def run(trials: int, chunk: int = 28416, seed: int = 2026, variant: str = "throughput"):
+    """variant: which blind rotation every batch goes through -- throughput (up to 4 PBS per CTA; what wide batches
+    get), latency (one PBS per CTA; what the narrow levels of a match get) or cluster (one PBS per pair of SMs)"""
     ck = fb.ClientKey.load(os.path.join(ROOT, "tests", "golden", "client_key"))
     ksk, bsk = fb.keygen_server_raw(ck, seed=0)
     sk = fb.ServerKey(ksk, bsk)
+    sk.set_cluster_threshold((1 << 30) if variant == "cluster" else 0)
+    sk.set_latency_threshold((1 << 30) if variant == "latency" else 0)
     fs = [lambda x: x, lambda x: (5 * x + 3) % 16, lambda x: int(x == 7), lambda x: int(x >= 1), lambda x: int(x > 9), lambda x: 15 - x,
           lambda x: int(x == 2), lambda x: int(x < 2)]
     luts = np.stack([fb.make_lut(f) for f in fs])
@@ -55,13 +59,14 @@ def run(trials: int, chunk: int = 28416, seed: int = 2026):
     sk.close()
     mean = s1 / done
     var = s2 / done - mean * mean
-    return {"trials": done, "decryption_failures": fails, "err_mean": mean, "err_std": var ** 0.5, "err_var": var, "err_abs_max": amax,
+    return {"variant": variant, "trials": done, "decryption_failures": fails, "err_mean": mean, "err_std": var ** 0.5, "err_var": var, "err_abs_max": amax,
             "expected_std_bound": 3.7e-5, "half_box": 1.0 / 32, "wall_s": time.time() - t0, "pbs_call_s": gpu_s}
 
 
 if __name__ == "__main__":
     trials = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 1000000
-    res = run(trials)
+    variant = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else "throughput"
+    res = run(trials, variant=variant)
     print(json.dumps(res))
     if "--json" in sys.argv:
         with open(sys.argv[sys.argv.index("--json") + 1], "w") as f:
