@@ -348,12 +348,21 @@ extern "C" int fb_pbs_batch(fb_ctx* ctx, const uint64_t* h_in, const uint64_t* h
   const uint32_t* d_idx = (const uint32_t*)ctx->lut_idx.p;
   // Large batches are pipelined in at most three chunks of whole throughput waves: the upload of chunk k+1 and the
   // download of chunk k-1 run on their own streams (two DMA engines) under the bootstraps of chunk k, so only the
-  // first upload and the last download are exposed.  Few, large chunks: every extra launch ends in a tail where
-  // SMs wait for the slowest CTA (measured: 12 chunks of 4 waves cost more than the copies they hide).
+  // first upload and the last download are exposed -- hence a short first and a short last chunk (4 waves each)
+  // around one long one.  Few chunks: every extra launch ends in a tail where SMs wait for the slowest CTA
+  // (measured: 12 chunks of 4 waves cost more than the copies they hide).
   const size_t q = (size_t)ctx->quantum;
-  const size_t third = ((count + 2) / 3 + q - 1) / q * q;
-  const size_t chunk = std::max(8 * q, third);
-  const size_t n_chunks = (count + chunk - 1) / chunk;
+  size_t bounds[4] = {0, count, count, count};
+  size_t n_chunks = 1;
+  if (count >= 16 * q) {
+    const size_t mid = (count - 8 * q) / q * q;
+    bounds[1] = 4 * q;
+    bounds[2] = 4 * q + mid;
+    n_chunks = 3;
+  } else if (count > 8 * q) {
+    bounds[1] = (count / 2 + q - 1) / q * q;
+    n_chunks = 2;
+  }
   if (n_chunks < 2) {
     FB_CUDA(ctx, cudaMemcpyAsync(d_in, h_in, count * FB_LWE_BIG_WORDS * 8, cudaMemcpyHostToDevice, ctx->stream));
     if ((rc = fb_pbs_batch_dev(ctx, d_in, (const uint64_t*)ctx->luts.p, d_idx, count, d_out))) return rc;
@@ -375,13 +384,13 @@ extern "C" int fb_pbs_batch(fb_ctx* ctx, const uint64_t* h_in, const uint64_t* h
   FB_CUDA(ctx, cudaStreamWaitEvent(ctx->h2d_stream, start, 0));
   FB_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h_stream, start, 0));
   for (size_t k = 0; k < n_chunks; k++) {
-    const size_t off = k * chunk, n = std::min(chunk, count - off);
+    const size_t off = bounds[k], n = bounds[k + 1] - bounds[k];
     FB_CUDA(ctx, cudaMemcpyAsync(d_in + off * FB_LWE_BIG_WORDS, h_in + off * FB_LWE_BIG_WORDS, n * FB_LWE_BIG_WORDS * 8,
                                  cudaMemcpyHostToDevice, ctx->h2d_stream));
     FB_CUDA(ctx, cudaEventRecord(ctx->pipe_events[2 * k], ctx->h2d_stream));
   }
   for (size_t k = 0; k < n_chunks; k++) {
-    const size_t off = k * chunk, n = std::min(chunk, count - off);
+    const size_t off = bounds[k], n = bounds[k + 1] - bounds[k];
     FB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->pipe_events[2 * k], 0));
     if ((rc = fb_pbs_batch_dev(ctx, d_in + off * FB_LWE_BIG_WORDS, (const uint64_t*)ctx->luts.p, d_idx + off, n, d_out + off * FB_LWE_BIG_WORDS)))
       return rc;

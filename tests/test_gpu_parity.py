@@ -199,11 +199,12 @@ def test_blind_rotation_variants_agree(client_key, gpu_key):
         assert np.abs(tfhe.torus_err(tfhe.phase_batch(client_key.big, outs[name]), ph_t)).max() < 2 * PBS_ERR_MAX, name
 
 
-def test_pbs_batch_pipelined_chunks(fck, gpu_key):
-    """fb_pbs_batch splits batches beyond 8 throughput quanta into chunks whose copies overlap the bootstraps:
-    every chunk, both sides of every chunk boundary and the ragged tail must come back right"""
+@pytest.mark.parametrize("quanta,extra", [(8, 1), (11, 300), (20, 37)])
+def test_pbs_batch_pipelined_chunks(quanta, extra, fck, gpu_key):
+    """fb_pbs_batch splits batches beyond 8 throughput quanta into two or three chunks whose copies overlap the
+    bootstraps: every chunk, both sides of every possible chunk boundary and the ragged tail must come back right"""
     q = gpu_key.pbs_quantum()
-    count = 2 * 8 * q + 8 * q // 2 + 37                     # three chunks, the last one ragged
+    count = quanta * q + extra
     base_msgs = (np.arange(128) * 5 + 1) % 16
     base = fck.encrypt_blocks(base_msgs, seed=91)
     cts = np.ascontiguousarray(np.tile(base, ((count + 127) // 128, 1))[:count])
@@ -212,12 +213,9 @@ def test_pbs_batch_pipelined_chunks(fck, gpu_key):
     luts = np.stack([fb.make_lut(f) for f in fs])
     idx = (np.arange(count) % 3).astype(np.uint32)
     out = gpu_key.pbs(cts, luts, idx)
-    third = ((count + 2) // 3 + q - 1) // q * q
-    chunk = max(8 * q, third)
-    pick = {0, 1, count - 1, count - 2, count // 2}
-    for b in range(chunk, count, chunk):
-        pick |= {b - 1, b, b + 1}
-    pick |= set(range(0, count, 997))
+    pick = {0, 1, count - 1, count - 2, count // 2} | set(range(0, count, 997))
+    for b in range(q, count, q):                       # chunk boundaries are multiples of the quantum
+        pick |= {b - 1, b, min(b + 1, count - 1)}
     for i in sorted(pick):
         assert fck.decrypt_block(out[i]) == fs[int(idx[i])](int(msgs[i])) & 15, (count, i)
 
