@@ -392,8 +392,12 @@ extern "C" int fb_pbs_batch(fb_ctx* ctx, const uint64_t* h_in, const uint64_t* h
   for (size_t k = 0; k < n_chunks; k++) {
     const size_t off = bounds[k], n = bounds[k + 1] - bounds[k];
     FB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->pipe_events[2 * k], 0));
-    if ((rc = fb_pbs_batch_dev(ctx, d_in + off * FB_LWE_BIG_WORDS, (const uint64_t*)ctx->luts.p, d_idx + off, n, d_out + off * FB_LWE_BIG_WORDS)))
+    if ((rc = fb_pbs_batch_dev(ctx, d_in + off * FB_LWE_BIG_WORDS, (const uint64_t*)ctx->luts.p, d_idx + off, n, d_out + off * FB_LWE_BIG_WORDS))) {
+      cudaStreamSynchronize(ctx->h2d_stream);   // nothing of this call may still touch the caller's buffers
+      cudaStreamSynchronize(ctx->d2h_stream);
+      cudaStreamSynchronize(ctx->stream);
       return rc;
+    }
     FB_CUDA(ctx, cudaEventRecord(ctx->pipe_events[2 * k + 1], ctx->stream));
     FB_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h_stream, ctx->pipe_events[2 * k + 1], 0));
     FB_CUDA(ctx, cudaMemcpyAsync(h_out + off * FB_LWE_BIG_WORDS, d_out + off * FB_LWE_BIG_WORDS, n * FB_LWE_BIG_WORDS * 8,
