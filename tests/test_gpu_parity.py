@@ -234,6 +234,27 @@ def test_has_match_reference_vectors_trivial(case, fck, gpu_key):
     assert fck.decrypt(res) == case["expected"]
 
 
+RANDOM_PATTERNS = ["/a+b?c/", "/ab{2,4}c/", r"/[a-d][^x-z]\./", "/abc/i", "/^a*b+$/", "/(ab|c)+x/", "/[^ab]+c/", "/a{,2}b/",
+                   "/[a-c]{2,}x?$/", "/^.a.$/", "/a|b|c/", "/[abc][^a-b]c{2}/", "/x[ab]+y/i", "/aaaa+/", "/a.+b/", "/(a|b)?c$/"]
+
+
+def test_has_match_random_patterns_on_the_device(fck, gpu_key):
+    """the device executes what the plaintext dry run of the plan promises: random (pattern, content) pairs on trivial
+    ciphertexts (the reference's own test style, engine.rs:282-286: no CMUX runs, a match takes milliseconds), singly
+    and as has_match_many batches, against the oracle"""
+    import random
+    rnd = random.Random(23)
+    for it in range(60):
+        pat = rnd.choice(RANDOM_PATTERNS)
+        max_n = 8 if "|" in pat and ("+" in pat or "*" in pat) else 40
+        n = rnd.randint(1, max_n)
+        contents = ["".join(rnd.choice("abcxyAB.") for _ in range(n)) for _ in range(rnd.randint(1, 5))]
+        exp = [rp.has_match(c, pat) for c in contents]
+        assert fck.decrypt(fb.has_match(gpu_key, fb.trivial_str(contents[0]), pat)) == exp[0], (pat, contents[0])
+        outs = fb.has_match_many(gpu_key, np.stack([fb.trivial_str(c) for c in contents]), pat)
+        assert [fck.decrypt(o) for o in outs] == exp, (pat, contents)
+
+
 REAL_CASES = [
     ("abc", "/^abc$/"), ("abd", "/^abc$/"),
     ("aBc", "/^abc$/i"), ("aBc" + "x" * 13, "/^abc$/i"), ("xxaBcxxxxxxxxxxx", "/abc/i"),
