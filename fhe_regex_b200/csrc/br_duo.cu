@@ -206,7 +206,8 @@ int br_duo_max_clusters() {
 cudaError_t launch_blind_rotate_duo(const c2* fbsk, const uint64_t* small, const uint64_t* luts, const uint32_t* lut_idx,
                                     uint64_t* out, const int32_t* out_rows, const c2* dtab, int count, cudaStream_t st) {
   if (count <= 0) return cudaSuccess;
-  static bool configured = false;
+  static PerDeviceOnce once;
+  bool& configured = *once.slot();
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(blind_rotate_duo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDuoSmem);
     if (e != cudaSuccess) return e;

@@ -153,7 +153,8 @@ void br_wide_make_table(c2* host_tab) { wide::make_wide_table(host_tab); }
 cudaError_t launch_blind_rotate_wide(const c2* fbsk, const uint64_t* small, const uint64_t* luts, const uint32_t* lut_idx,
                                      uint64_t* out, const int32_t* out_rows, const c2* wtab, int count, cudaStream_t st) {
   if (count <= 0) return cudaSuccess;
-  static bool configured = false;
+  static PerDeviceOnce once;
+  bool& configured = *once.slot();
   static int skew = 200;   // cycles; measured on B200: 0 -> 2.46 ms, 100..300 -> 2.38-2.40 ms per 148-PBS wave
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(blind_rotate_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWideSmem);

@@ -375,7 +375,8 @@ template <int S>
 static cudaError_t launch_br_s(const c2* fbsk, const uint64_t* small, const uint64_t* luts, const uint32_t* lut_idx,
                                uint64_t* out, const int32_t* out_rows, const c2* tabs, int count, cudaStream_t st) {
   const size_t smem = br_smem_bytes(S);
-  static bool configured = false;
+  static PerDeviceOnce once;
+  bool& configured = *once.slot();
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(blind_rotate_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

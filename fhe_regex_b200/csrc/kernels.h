@@ -5,6 +5,16 @@
 #include "br_core.cuh"
 
 namespace fb {
+// cudaFuncSetAttribute is per device: one flag per (kernel, device), so a process driving several GPUs (one context
+// each) configures every kernel on each of them
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool* slot() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return &done[d & 63];
+  }
+};
 size_t br_smem_bytes(int S);
 cudaError_t launch_bsk_convert(const uint64_t* bsk_std, c2* fbsk, const c2* tabs, cudaStream_t st);
 cudaError_t launch_blind_rotate(const c2* fbsk, const uint64_t* small, const uint64_t* luts, const uint32_t* lut_idx,

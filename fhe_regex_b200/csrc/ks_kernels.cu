@@ -219,7 +219,8 @@ cudaError_t launch_keyswitch_mma(const uint8_t* kb, int8_t* dig, const uint64_t*
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   constexpr int smem = KS_STAGES * (KS_BM + KS_BN) * KS_BK;  // 65536
-  static bool configured = false;
+  static PerDeviceOnce once;
+  bool& configured = *once.slot();
   if (!configured) {
     e = cudaFuncSetAttribute(ks_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
