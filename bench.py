@@ -390,24 +390,39 @@ def main():
         # many contents against one pattern in shared launches (fb_has_match_many): the levels are wide enough for
         # the throughput kernel, a match costs its PBS at the throughput rate instead of one latency per level
         many = []
-        if world == 1:
-            for n_chars, m, pattern in ((64, 64, "/a+b?c/"), (256, 16, "/a+b?c/")):
-                rng2 = np.random.default_rng(11)
-                # distinct contents: 4 at 64 characters; at 256 the no-match content of the single-match record and a
-                # copy of it with a match planted at the end (2 oracle runs of ~9 s are enough)
-                distinct = (["".join(rng2.choice(list("abcx"), size=n_chars)) for _ in range(4)] if n_chars == 64
-                            else [c256, c256[:-3] + "abc"])
-                base = [fb.encrypt_str(ck, t_, seed=20 + i) for i, t_ in enumerate(distinct)]
-                texts = [distinct[i % len(distinct)] for i in range(m)]
-                cts = np.stack([base[i % len(distinct)] for i in range(m)])
-                fb.has_match_many(sk, cts, pattern)
-                tm = time.perf_counter()
-                outs, st = fb.has_match_many(sk, cts, pattern, return_stats=True)
-                wall = (time.perf_counter() - tm) * 1e3
-                got = [ck.decrypt(o) for o in outs]
-                assert got == [expected(t_, pattern) for t_ in texts], (pattern, got)
-                many.append({"pattern": pattern, "n_chars": n_chars, "contents": m, "ms_total": wall, "ms_per_match": wall / m,
-                             "gpu_ms_total": st["gpu_ms"], "pbs_per_match": st["pbs"], "matches_per_s": m / (wall * 1e-3)})
+        # every rank matches its own m contents (weak scaling: documents are independent, no collective on the data path)
+        for n_chars, m, pattern in ((64, 64, "/a+b?c/"), (256, 16, "/a+b?c/")):
+            rng2 = np.random.default_rng(11)
+            # distinct contents: 4 at 64 characters; at 256 the no-match content of the single-match record and a
+            # copy of it with a match planted at the end (2 oracle runs of ~9 s are enough)
+            distinct = (["".join(rng2.choice(list("abcx"), size=n_chars)) for _ in range(4)] if n_chars == 64
+                        else [c256, c256[:-3] + "abc"])
+            base = [fb.encrypt_str(ck, t_, seed=20 + i) for i, t_ in enumerate(distinct)]
+            texts = [distinct[i % len(distinct)] for i in range(m)]
+            cts = np.stack([base[i % len(distinct)] for i in range(m)])
+            fb.has_match_many(sk, cts, pattern)
+            barrier()
+            tm = time.perf_counter()
+            outs, st = fb.has_match_many(sk, cts, pattern, return_stats=True)
+            barrier()
+            wall = (time.perf_counter() - tm) * 1e3
+            got = [int(ck.decrypt(o)) for o in outs]
+            if world > 1:     # the ranks hold the same contents: rank 0 checks everybody's decryptions against the oracle
+                mine = torch.tensor(got, dtype=torch.int64, device=dev)
+                allgot = torch.empty((world, m), dtype=torch.int64, device=dev)
+                dist.all_gather_into_tensor(allgot, mine)
+                tw = torch.tensor([wall], dtype=torch.float64, device=dev)
+                dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+                wall = float(tw[0])
+                got_all = allgot.cpu().tolist()
+            else:
+                got_all = [got]
+            if rank == 0:
+                exp_list = [expected(t_, pattern) for t_ in texts]
+                assert all(g == exp_list for g in got_all), (pattern, got_all)
+                many.append({"pattern": pattern, "n_chars": n_chars, "contents_per_gpu": m, "contents": m * world, "ms_total": wall,
+                             "ms_per_match": wall / (m * world), "gpu_ms_total_rank0": st["gpu_ms"], "pbs_per_match": st["pbs"],
+                             "matches_per_s": m * world / (wall * 1e-3)})
         if rank == 0:
             line["match_many"] = many
             line["match"] = matches
