@@ -21,6 +21,7 @@ namespace fb {
 
 namespace {
 constexpr int kStageBytes = 4 * kHalfN * (int)sizeof(c2);  // 65536
+// kMacPrefetch (template parameter of the kernel): groups of 4 GGSW values a thread fetches before the pre-MAC barrier
 constexpr int kBufBytes = 2 * kHalfN * (int)sizeof(c2);    // 32768
 constexpr size_t kOffBufA = 2 * (size_t)kStageBytes;
 constexpr size_t kOffBufB = kOffBufA + kBufBytes;
@@ -33,6 +34,7 @@ constexpr size_t kWideSmem = kOffBars + 2 * sizeof(uint64_t) + 16;
 
 __device__ __forceinline__ void half_sync(int P) { asm volatile("bar.sync %0, 128;" ::"r"(1 + P) : "memory"); }
 
+template <int kMacPrefetch>
 __global__ void __launch_bounds__(wide::kThreads, 1)
 blind_rotate_wide_kernel(const c2* __restrict__ fbsk, const uint64_t* __restrict__ small, const uint64_t* __restrict__ luts,
                          const uint32_t* __restrict__ lut_idx, uint64_t* __restrict__ out, const int32_t* __restrict__ out_rows,
@@ -116,9 +118,14 @@ blind_rotate_wide_kernel(const c2* __restrict__ fbsk, const uint64_t* __restrict
     wide::fwd_stage2(bufA_p, bufB_p, t, tw);
     half_sync(P);
     wide::fwd_stage3(bufB_p, bufA_p, t);
-    __syncthreads();                              // both spectra complete
+    // the staged GGSW does not depend on the other warps: wait for it and fetch half of this thread's values before the
+    // barrier, so that their shared-memory latency falls into the barrier wait
     mbar_wait(full_bar + (n & 1), (uint32_t)(n >> 1) & 1u);
-    wide::mac_inv_stage1(bufA, bufA + kHalfN, reinterpret_cast<const c2*>(smem + (size_t)(n & 1) * kStageBytes), P, t, tw, bufB_p);
+    const c2* ggsw = reinterpret_cast<const c2*>(smem + (size_t)(n & 1) * kStageBytes);
+    c2 gpre[4 * (kMacPrefetch > 0 ? kMacPrefetch : 1)];
+    wide::mac_prefetch<kMacPrefetch>(ggsw, P, t, gpre);
+    __syncthreads();                              // both spectra complete
+    wide::mac_inv_stage1<kMacPrefetch>(bufA, bufA + kHalfN, ggsw, gpre, P, t, tw, bufB_p);
     __syncthreads();                              // nobody reads bufA (or this GGSW stage) any more
     // the halves leave this barrier in phase; holding one back by a fraction of a stage makes its shared-memory
     // bursts fall into the other half's arithmetic for the six per-half stages until they meet again
@@ -150,20 +157,36 @@ blind_rotate_wide_kernel(const c2* __restrict__ fbsk, const uint64_t* __restrict
 size_t br_wide_table_bytes() { return (size_t)wide::kTabC2 * sizeof(c2); }
 void br_wide_make_table(c2* host_tab) { wide::make_wide_table(host_tab); }
 
+template <int NPRE>
+static cudaError_t launch_wide_n(const c2* fbsk, const uint64_t* small, const uint64_t* luts, const uint32_t* lut_idx, uint64_t* out,
+                                 const int32_t* out_rows, const c2* wtab, int count, int skew, cudaStream_t st) {
+  static PerDeviceOnce once;
+  bool& configured = *once.slot();
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(blind_rotate_wide_kernel<NPRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWideSmem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  blind_rotate_wide_kernel<NPRE><<<count, wide::kThreads, kWideSmem, st>>>(fbsk, small, luts, lut_idx, out, out_rows, wtab, count, skew);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_blind_rotate_wide(const c2* fbsk, const uint64_t* small, const uint64_t* luts, const uint32_t* lut_idx,
                                      uint64_t* out, const int32_t* out_rows, const c2* wtab, int count, cudaStream_t st) {
   if (count <= 0) return cudaSuccess;
-  static PerDeviceOnce once;
-  bool& configured = *once.slot();
-  static int skew = 200;   // cycles; measured on B200: 0 -> 2.46 ms, 100..300 -> 2.38-2.40 ms per 148-PBS wave
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(blind_rotate_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWideSmem);
-    if (e != cudaSuccess) return e;
-    configured = true;
+  static int skew = -1, npre = 3;   // GGSW groups fetched before the pre-MAC barrier: 0 -> 2.44 ms, 1/2 -> 2.40, 3 -> 2.30, 4 -> 2.39 (254 registers)
+  if (skew < 0) {   // cycles; measured on B200: 0 -> 2.46 ms, 100..300 -> 2.38-2.40 ms per 148-PBS wave
+    skew = 200;
     if (const char* e2 = getenv("FB_WIDE_SKEW")) skew = atoi(e2);
+    if (const char* e3 = getenv("FB_WIDE_PREFETCH")) npre = atoi(e3);
   }
-  blind_rotate_wide_kernel<<<count, wide::kThreads, kWideSmem, st>>>(fbsk, small, luts, lut_idx, out, out_rows, wtab, count, skew);
-  return cudaGetLastError();
+  switch (npre) {
+    case 0: return launch_wide_n<0>(fbsk, small, luts, lut_idx, out, out_rows, wtab, count, skew, st);
+    case 1: return launch_wide_n<1>(fbsk, small, luts, lut_idx, out, out_rows, wtab, count, skew, st);
+    case 4: return launch_wide_n<4>(fbsk, small, luts, lut_idx, out, out_rows, wtab, count, skew, st);
+    case 2: return launch_wide_n<2>(fbsk, small, luts, lut_idx, out, out_rows, wtab, count, skew, st);
+    default: return launch_wide_n<3>(fbsk, small, luts, lut_idx, out, out_rows, wtab, count, skew, st);
+  }
 }
 
 }  // namespace fb

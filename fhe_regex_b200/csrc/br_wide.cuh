@@ -162,7 +162,23 @@ FB_HD void fwd_stage3(const c2* in, c2* out, int t) {
 
 // forward stage 4 (a+b, a-b) of both polynomials + Fourier MAC with the staged GGSW + inverse stage 1.
 // Thread (column qo, t) produces out_qo[k] = X_0[k] G[0][qo][k] + X_1[k] G[1][qo][k] for k = t + 128 m.
-FB_HD void mac_inv_stage1(const c2* in0, const c2* in1, const c2* ggsw, int qo, int t, const Tw& tw, c2* out) {
+// The GGSW values do not depend on the other threads: the first NPRE of the four groups (4 values each) may be
+// fetched before the barrier that precedes this stage (mac_prefetch) and are then passed in gpre.
+template <int NPRE>
+FB_HD void mac_prefetch(const c2* ggsw, int qo, int t, c2 (&gpre)[4 * (NPRE > 0 ? NPRE : 1)]) {
+  const c2* g0 = ggsw + (size_t)(0 * 2 + qo) * kHalfN;
+  const c2* g1 = ggsw + (size_t)(1 * 2 + qo) * kHalfN;
+#pragma unroll
+  for (int u = 0; u < NPRE; u++) {
+    const int k = t + 128 * u;
+    gpre[4 * u] = g0[k];
+    gpre[4 * u + 1] = g1[k];
+    gpre[4 * u + 2] = g0[k + 512];
+    gpre[4 * u + 3] = g1[k + 512];
+  }
+}
+template <int NPRE>
+FB_HD void mac_inv_stage1(const c2* in0, const c2* in1, const c2* ggsw, const c2* gpre, int qo, int t, const Tw& tw, c2* out) {
   c2 o[8];
   const c2* g0 = ggsw + (size_t)(0 * 2 + qo) * kHalfN;
   const c2* g1 = ggsw + (size_t)(1 * 2 + qo) * kHalfN;
@@ -172,7 +188,8 @@ FB_HD void mac_inv_stage1(const c2* in0, const c2* in1, const c2* ggsw, int qo, 
     const c2 a0 = in0[swz(k)], b0 = in0[swz(k + 512)];
     const c2 a1 = in1[swz(k)], b1 = in1[swz(k + 512)];
     const c2 x0l = cadd(a0, b0), x0h = csub(a0, b0), x1l = cadd(a1, b1), x1h = csub(a1, b1);
-    const c2 gl0 = g0[k], gl1 = g1[k], gh0 = g0[k + 512], gh1 = g1[k + 512];
+    const c2 gl0 = u < NPRE ? gpre[4 * u] : g0[k], gl1 = u < NPRE ? gpre[4 * u + 1] : g1[k];
+    const c2 gh0 = u < NPRE ? gpre[4 * u + 2] : g0[k + 512], gh1 = u < NPRE ? gpre[4 * u + 3] : g1[k + 512];
     o[u].x = fb_fma(-x1l.y, gl1.y, fb_fma(x1l.x, gl1.x, fb_fma(-x0l.y, gl0.y, x0l.x * gl0.x)));
     o[u].y = fb_fma(x1l.y, gl1.x, fb_fma(x1l.x, gl1.y, fb_fma(x0l.y, gl0.x, x0l.x * gl0.y)));
     o[u + 4].x = fb_fma(-x1h.y, gh1.y, fb_fma(x1h.x, gh1.x, fb_fma(-x0h.y, gh0.y, x0h.x * gh0.x)));

@@ -109,7 +109,7 @@ extern "C" void emu_wide_blind_rotate(const c2* fbsk, const uint64_t* small, con
     for (int tid = 0; tid < 256; tid++) fwd_stage1(c.acc.data() + (tid >> 7) * kN, c.own[tid], a, tid & 127, c.tw[tid], c.bufA.data() + (tid >> 7) * kHalfN);
     forward_tail(c);
     for (int tid = 0; tid < 256; tid++)
-      mac_inv_stage1(c.bufA.data(), c.bufA.data() + kHalfN, ggsw, tid >> 7, tid & 127, c.tw[tid], c.bufB.data() + (tid >> 7) * kHalfN);
+      mac_inv_stage1<0>(c.bufA.data(), c.bufA.data() + kHalfN, ggsw, nullptr, tid >> 7, tid & 127, c.tw[tid], c.bufB.data() + (tid >> 7) * kHalfN);
     inverse_tail(c);
     for (int tid = 0; tid < 256; tid++) phaseC_accumulate(c.bufB.data() + (tid >> 7) * kHalfN, tid & 127, c.own[tid], c.acc.data() + (tid >> 7) * kN);
   }
