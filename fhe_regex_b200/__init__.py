@@ -85,9 +85,11 @@ def lib():
     L.fb_has_match_many.argtypes = [vp, vp, sz, sz, C.c_char_p, vp, C.POINTER(MatchStats)]
     L.fb_or_fold.argtypes = [vp, vp, sz, vp]
     L.fb_parse_debug.argtypes = [C.c_char_p, C.c_char_p, sz]
-    L.fb_plan_stats.argtypes = [C.c_char_p, sz, C.POINTER(MatchStats)]
-    L.fb_plan_level_widths.argtypes = [C.c_char_p, sz, C.c_int, C.c_int, vp, sz]
-    L.fb_plan_eval_plain.argtypes = [C.c_char_p, vp, sz, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    L.fb_plan_stats.argtypes = [C.c_char_p, sz, C.c_uint32, C.POINTER(MatchStats)]
+    L.fb_plan_level_widths.argtypes = [C.c_char_p, sz, C.c_int, C.c_int, C.c_uint32, vp, sz]
+    L.fb_plan_eval_plain.argtypes = [C.c_char_p, vp, sz, C.c_int, C.c_int, C.c_uint32, C.POINTER(C.c_int)]
+    L.fb_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
+    L.fb_get_option.argtypes = [vp, C.c_char_p, C.POINTER(C.c_int64)]
     L.fb_kernel_stats_reset.argtypes = [vp]
     L.fb_set_latency_threshold.argtypes = [vp, C.c_int]
     L.fb_set_cluster_threshold.argtypes = [vp, C.c_int]
@@ -136,29 +138,33 @@ def parse(pattern: str) -> str:
     return buf.value.decode("latin-1")
 
 
-def plan_stats(pattern: str, n_chars: int) -> dict:
+PLAN_REFERENCE_SHAPED = 1   # FB_PLAN_REFERENCE_SHAPED: evaluate every variant the reference enumerates
+
+
+def plan_stats(pattern: str, n_chars: int, reference_shaped: bool = False) -> dict:
     st = MatchStats()
-    rc = lib().fb_plan_stats(pattern.encode("latin-1"), n_chars, C.byref(st))
+    rc = lib().fb_plan_stats(pattern.encode("latin-1"), n_chars, PLAN_REFERENCE_SHAPED if reference_shaped else 0, C.byref(st))
     if rc != FB_OK:
         _raise(rc, "plan failed for %r" % pattern)
     return st.as_dict()
 
 
-def plan_level_widths(pattern: str, n_chars: int, rank: int = 0, world: int = 1) -> list:
+def plan_level_widths(pattern: str, n_chars: int, rank: int = 0, world: int = 1, reference_shaped: bool = False) -> list:
     """PBS batch width of every level of the lowered plan (host only)"""
     buf = np.zeros(256, dtype=np.int32)
-    n = lib().fb_plan_level_widths(pattern.encode(), n_chars, rank, world, _p(buf), buf.size)
+    n = lib().fb_plan_level_widths(pattern.encode(), n_chars, rank, world, PLAN_REFERENCE_SHAPED if reference_shaped else 0, _p(buf), buf.size)
     if n < 0:
         _raise(n, "plan_level_widths")
     return [int(x) for x in buf[:min(n, buf.size)]]
 
 
-def plan_eval_plain(pattern: str, content: str, rank: int = 0, world: int = 1) -> int:
+def plan_eval_plain(pattern: str, content: str, rank: int = 0, world: int = 1, reference_shaped: bool = False) -> int:
     """Dry run of the lowered PBS circuit on cleartext bytes (host only): the 0/1 decrypt would give."""
     b = content.encode("latin-1")
     raw = np.frombuffer(b, dtype=np.uint8) if len(b) else np.zeros(1, dtype=np.uint8)
     res = C.c_int(-1)
-    rc = lib().fb_plan_eval_plain(pattern.encode("latin-1"), _p(np.ascontiguousarray(raw)), len(b), rank, world, C.byref(res))
+    rc = lib().fb_plan_eval_plain(pattern.encode("latin-1"), _p(np.ascontiguousarray(raw)), len(b), rank, world,
+                                  PLAN_REFERENCE_SHAPED if reference_shaped else 0, C.byref(res))
     if rc != FB_OK:
         _raise(rc, "plan dry run failed for %r" % pattern)
     return res.value
@@ -332,6 +338,18 @@ class ServerKey:
         v = C.c_double(0)
         self._check(lib().fb_measure_fp64_peak(self._h, reps, C.byref(v)))
         return v.value
+
+    def set_option(self, name: str, value: int) -> int:
+        """fb_set_option: per-context knob (include/fhe_b200.h lists them); returns the previous value"""
+        prev = C.c_int64(0)
+        self._check(lib().fb_get_option(self._h, name.encode(), C.byref(prev)))
+        self._check(lib().fb_set_option(self._h, name.encode(), int(value)))
+        return int(prev.value)
+
+    def get_option(self, name: str) -> int:
+        v = C.c_int64(0)
+        self._check(lib().fb_get_option(self._h, name.encode(), C.byref(v)))
+        return int(v.value)
 
     def set_latency_threshold(self, max_count: int) -> int:
         """batches of up to max_count PBS use the one-PBS-per-CTA blind rotation; returns the previous value"""

@@ -64,11 +64,9 @@ extern "C" int fb_ctx_create(fb_ctx** out, int device) {
   fb::make_twiddle_tables(tabs.data(), tabs.data() + fb::kTabEntries * 32);
   fb::br_wide_make_table(tabs.data() + n_tabs);
   fb::br_duo_make_table(tabs.data() + n_tabs + n_wide);
-  if (const char* w = std::getenv("FB_WIDE_MAX")) ctx->wide_max = std::atoi(w);
   // measured on B200: a PBS on a pair of SMs takes 2.39 ms, on one SM 2.37 ms (the step is a chain of dependent
-  // stages, not bandwidth) -- the cluster kernel is kept as an option (FB_DUO_MAX, fb_set_cluster_threshold), off by default
+  // stages, not bandwidth) -- the cluster kernel is kept as an option (fb_set_cluster_threshold), off by default
   ctx->duo_pairs = fb::br_duo_max_clusters();
-  if (const char* w = std::getenv("FB_DUO_MAX")) ctx->duo_max = std::atoi(w);
   if (cudaMalloc(&ctx->d_tabs, tabs.size() * sizeof(c2)) != cudaSuccess ||
       cudaMemcpy(ctx->d_tabs, tabs.data(), tabs.size() * sizeof(c2), cudaMemcpyHostToDevice) != cudaSuccess) {
     delete ctx;
@@ -219,7 +217,7 @@ int fb_run_blind_rotate(fb_ctx* ctx, const uint64_t* d_small, const uint64_t* d_
   auto narrow = [&](const uint64_t* sm, const uint32_t* li, uint64_t* o, const int32_t* orows, int n) {
     return (n <= ctx->duo_max)
                ? fb::launch_blind_rotate_duo(ctx->d_fbsk, sm, d_luts, li, o, orows, ctx->d_dtab, n, ctx->stream)
-               : fb::launch_blind_rotate_wide(ctx->d_fbsk, sm, d_luts, li, o, orows, ctx->d_wtab, n, ctx->stream);
+               : fb::launch_blind_rotate_wide(ctx->d_fbsk, sm, d_luts, li, o, orows, ctx->d_wtab, n, ctx->wide_skew, ctx->wide_prefetch, ctx->stream);
   };
   const int narrow_max = ctx->wide_max > ctx->duo_max ? ctx->wide_max : ctx->duo_max;
   cudaError_t e;
@@ -229,7 +227,10 @@ int fb_run_blind_rotate(fb_ctx* ctx, const uint64_t* d_small, const uint64_t* d_
     const int q = ctx->quantum;
     const int tail = (q > 0) ? count % q : 0;
     const int head = (tail > 0 && tail <= narrow_max) ? count - tail : count;
-    e = fb::launch_blind_rotate(ctx->d_fbsk, d_small, d_luts, d_lut_idx, d_out, d_out_rows, ctx->d_tabs, head, ctx->stream);
+    // the fused body is built for 4 PBS per SM: batches that do not fill the GPU at that width keep the phase-by-phase body
+    const bool fused = ctx->br_variant >= 1 && head > 3 * (q / fb::br_samples_per_cta());
+    e = fused ? fb::launch_blind_rotate_fused(ctx->d_fbsk, d_small, d_luts, d_lut_idx, d_out, d_out_rows, ctx->d_tabs, head, ctx->br_variant - 1, ctx->stream)
+              : fb::launch_blind_rotate(ctx->d_fbsk, d_small, d_luts, d_lut_idx, d_out, d_out_rows, ctx->d_tabs, head, ctx->stream);
     if (e == cudaSuccess && head < count)
       e = narrow(d_small + (size_t)head * FB_LWE_SMALL_WORDS, d_lut_idx + head, d_out_rows ? d_out : d_out + (size_t)head * FB_LWE_BIG_WORDS,
                  d_out_rows ? d_out_rows + head : nullptr, tail);
@@ -281,6 +282,64 @@ extern "C" int fb_set_cluster_threshold(fb_ctx* ctx, int max_count) {
   ctx->duo_max = max_count;
   return prev;
 }
+// ---- options: every knob of the library is per context and set explicitly (nothing is read from the environment) ----
+namespace {
+struct OptionDesc { const char* name; int64_t lo, hi; };
+const OptionDesc kOptions[] = {
+    {"latency_threshold", 0, 1 << 30},      // = fb_set_latency_threshold
+    {"cluster_threshold", 0, 1 << 30},      // = fb_set_cluster_threshold
+    {"br_variant", 0, 2},                   // throughput blind rotation: 0 phase-by-phase body, 1 fused body, 2 fused + digits via I2F
+    {"wide_skew", 0, 100000},               // latency kernel: hold-back of one CTA half after the MAC, cycles
+    {"wide_prefetch", 0, 4},                // latency kernel: GGSW groups fetched before the pre-MAC barrier
+    {"plan_reference_shaped", 0, 1},        // 1: evaluate every variant the reference enumerates (no absorption)
+    {"plan_timing", 0, 1},                  // 1: planner phase times on stderr
+};
+int64_t* option_slot(fb_ctx* ctx, const char* name, int64_t& shadow, int& which) {
+  for (int i = 0; i < (int)(sizeof(kOptions) / sizeof(kOptions[0])); i++)
+    if (std::strcmp(name, kOptions[i].name) == 0) {
+      which = i;
+      switch (i) {
+        case 0: shadow = ctx->wide_max; break;
+        case 1: shadow = ctx->duo_max; break;
+        case 2: shadow = ctx->br_variant; break;
+        case 3: shadow = ctx->wide_skew; break;
+        case 4: shadow = ctx->wide_prefetch; break;
+        case 5: shadow = ctx->plan_absorb ? 0 : 1; break;
+        case 6: shadow = ctx->plan_timing ? 1 : 0; break;
+      }
+      return &shadow;
+    }
+  return nullptr;
+}
+}  // namespace
+
+extern "C" int fb_get_option(fb_ctx* ctx, const char* name, int64_t* value) {
+  if (!ctx || !name || !value) return fb_fail(ctx, FB_ERR_ARG, "null argument");
+  int64_t cur = 0;
+  int which = -1;
+  if (!option_slot(ctx, name, cur, which)) return fb_fail(ctx, FB_ERR_ARG, std::string("unknown option: ") + name);
+  *value = cur;
+  return FB_OK;
+}
+
+extern "C" int fb_set_option(fb_ctx* ctx, const char* name, int64_t value) {
+  if (!ctx || !name) return fb_fail(ctx, FB_ERR_ARG, "null argument");
+  int64_t cur = 0;
+  int which = -1;
+  if (!option_slot(ctx, name, cur, which)) return fb_fail(ctx, FB_ERR_ARG, std::string("unknown option: ") + name);
+  if (value < kOptions[which].lo || value > kOptions[which].hi) return fb_fail(ctx, FB_ERR_ARG, std::string("option out of range: ") + name);
+  switch (which) {
+    case 0: ctx->wide_max = (int)value; break;
+    case 1: ctx->duo_max = (int)value; break;
+    case 2: ctx->br_variant = (int)value; break;
+    case 3: ctx->wide_skew = (int)value; break;
+    case 4: ctx->wide_prefetch = (int)value; break;
+    case 5: ctx->plan_absorb = value == 0; break;
+    case 6: ctx->plan_timing = value != 0; break;
+  }
+  return FB_OK;
+}
+
 extern "C" int fb_kernel_stats_reset(fb_ctx* ctx) {
   if (!ctx) return FB_ERR_ARG;
   int rc = resolve_pending(ctx);

@@ -43,6 +43,11 @@ FB_HD double fb_fma(double a, double b, double c) {
 
 #include "fft32_gen.h"
 
+template <int... Ns> struct fb_iseq {};
+template <int N, int... Ns> struct fb_make_iseq_impl : fb_make_iseq_impl<N - 1, N - 1, Ns...> {};
+template <int... Ns> struct fb_make_iseq_impl<0, Ns...> { typedef fb_iseq<Ns...> type; };
+template <int N> using fb_make_iseq = typename fb_make_iseq_impl<N>::type;
+
 namespace fb {
 
 constexpr int kLweN = 742;       // small LWE dimension
@@ -248,6 +253,76 @@ FB_HD void col_load_brev(double (&x)[32], const double* plane_p, int lane) {
     const int k1 = brev5(q);
     x[q] = plane_p[k1 * 32 + (lane ^ k1)];
   }
+}
+
+// ---- fused CMUX body (blind_rotate_fused_kernel, br_fused.cu) ------------------------------------------
+// The same arithmetic as above cut into pieces that interleave in program order: the decomposition of slot r
+// (shared-memory reads + integer work) with the butterflies of pass 1 that its digits make computable; the
+// Fourier MAC (shuffles + key reads) block by block between the last stages of forward pass 2 and the first
+// stages of inverse pass 1; the torus rounding / accumulation with the last-stage butterflies of inverse pass 2.
+// A warp then has FP64 work to issue while its shared-memory requests are in flight.
+
+// digits of slot R: coefficients 32R+lane (re) and 32R+lane+1024 (im) of acc*X^a - acc.
+// sm = base of the shared memory block, shp_off = byte offset of this polynomial's 8 KiB accumulator copy in it
+// (a multiple of 8192, so the masked rotation offset is OR-ed in); t0 = 4*((lane - a) mod 4096);
+// own = &acc[lane] (this thread's own words, 32 apart)
+// the same digit through the integer-to-double conversion unit (one instruction instead of XOR + move + DADD)
+FB_HD double pbs_digit32_cvt(uint32_t diff) {
+  const int32_t q = (int32_t)(diff + 256u) >> 9;
+#if defined(__CUDA_ARCH__)
+  return __int2double_rn(q);
+#else
+  return (double)q;
+#endif
+}
+template <int R, bool CVT = false>
+FB_HD void phaseA_slot(double& dr, double& di, const unsigned char* sm, uint32_t shp_off, uint32_t t0, const uint32_t* own) {
+  const uint32_t ta = t0 + 128u * R, tb = t0 + 128u * (R + 32);
+  uint32_t xa = *reinterpret_cast<const uint32_t*>(sm + ((ta & 8188u) | shp_off));
+  uint32_t xb = *reinterpret_cast<const uint32_t*>(sm + ((tb & 8188u) | shp_off));
+  if (ta & 8192u) xa = 0u - xa;
+  if (tb & 8192u) xb = 0u - xb;
+  if (CVT) {
+    dr = pbs_digit32_cvt(xa - own[32 * R]);
+    di = pbs_digit32_cvt(xb - own[32 * (R + 32)]);
+  } else {
+    dr = pbs_digit32(xa - own[32 * R]);
+    di = pbs_digit32(xb - own[32 * (R + 32)]);
+  }
+}
+template <int N, bool CVT>
+FB_HD void phaseA_f1_step(double (&xr)[32], double (&xi)[32], const unsigned char* sm, uint32_t shp_off, uint32_t t0, const uint32_t* own) {
+  constexpr int R = fb_f1_order(N);
+  phaseA_slot<R, CVT>(xr[R], xi[R], sm, shp_off, t0, own);
+  fft32_f1_step<N>(xr, xi);
+}
+template <bool CVT, int... Ns>
+FB_HD void phaseA_f1_seq(double (&xr)[32], double (&xi)[32], const unsigned char* sm, uint32_t shp_off, uint32_t t0, const uint32_t* own,
+                         fb_iseq<Ns...>) {
+  (phaseA_f1_step<Ns, CVT>(xr, xi, sm, shp_off, t0, own), ...);
+}
+// phase A + forward pass 1 (twist folded in): replaces phaseA_load32 + fft32_fwd_twist
+template <bool CVT = false>
+FB_HD void phaseA_f1(double (&xr)[32], double (&xi)[32], const unsigned char* sm, uint32_t shp_off, uint32_t a, int lane) {
+  const uint32_t t0 = (4u * (uint32_t)lane - 4u * a) & 16380u;
+  const uint32_t* own = reinterpret_cast<const uint32_t*>(sm + shp_off) + lane;
+  phaseA_f1_seq<CVT>(xr, xi, sm, shp_off, t0, own, fb_make_iseq<32>{});
+}
+
+// round(frac(k * ts) * 2^32) mod 2^32 in three FMAs, the pending factor k of the untwist folded in:
+// s1 = M + rint(k*ts); g = M - rint(k*ts)*2^32 (exact); s2 = (k*ts - rint(k*ts))*2^32 + M; |k*ts| < 2^51
+FB_HD uint32_t torus32_round_scaled(double ts, double k) {
+  const double kM = 6755399441055744.0;                                  // 1.5 * 2^52
+  const double kC = 6755399441055744.0 * 4294967296.0 + 6755399441055744.0;  // M * 2^32 + M (exact: 34 significant bits)
+  const double s1 = fb_fma(ts, k, kM);
+  const double g = fb_fma(s1, -4294967296.0, kC);
+  return double_lo32(fb_fma(ts, k * 4294967296.0, g));
+}
+// torus increments of slot R after fft32_i2_fin (pending untwist magnitudes and the 1/1024 of the transform)
+template <int R>
+FB_HD void phaseC_slot(const double (&xr)[32], const double (&xi)[32], uint32_t& inc0, uint32_t& inc1) {
+  inc0 = torus32_round_scaled(xr[R], fb_i2_kre(R) * (1.0 / 1024.0));
+  inc1 = torus32_round_scaled(xi[R], fb_i2_kim(R) * (1.0 / 1024.0));
 }
 
 // Host-side: twiddle tables.  tab_f[e][lane], tab_i[e][k1], e < 4: "lo" l = e; e >= 4: "hi" h = e-4.

@@ -172,14 +172,10 @@ static cudaError_t launch_wide_n(const c2* fbsk, const uint64_t* small, const ui
 }
 
 cudaError_t launch_blind_rotate_wide(const c2* fbsk, const uint64_t* small, const uint64_t* luts, const uint32_t* lut_idx,
-                                     uint64_t* out, const int32_t* out_rows, const c2* wtab, int count, cudaStream_t st) {
+                                     uint64_t* out, const int32_t* out_rows, const c2* wtab, int count, int skew, int npre, cudaStream_t st) {
   if (count <= 0) return cudaSuccess;
-  static int skew = -1, npre = 3;   // GGSW groups fetched before the pre-MAC barrier: 0 -> 2.44 ms, 1/2 -> 2.40, 3 -> 2.30, 4 -> 2.39 (254 registers)
-  if (skew < 0) {   // cycles; measured on B200: 0 -> 2.46 ms, 100..300 -> 2.38-2.40 ms per 148-PBS wave
-    skew = 200;
-    if (const char* e2 = getenv("FB_WIDE_SKEW")) skew = atoi(e2);
-    if (const char* e3 = getenv("FB_WIDE_PREFETCH")) npre = atoi(e3);
-  }
+  // npre = GGSW groups fetched before the pre-MAC barrier: 0 -> 2.44 ms, 1/2 -> 2.40, 3 -> 2.30, 4 -> 2.39 (254 registers);
+  // skew (cycles): measured on B200: 0 -> 2.46 ms, 100..300 -> 2.38-2.40 ms per 148-PBS wave
   switch (npre) {
     case 0: return launch_wide_n<0>(fbsk, small, luts, lut_idx, out, out_rows, wtab, count, skew, st);
     case 1: return launch_wide_n<1>(fbsk, small, luts, lut_idx, out, out_rows, wtab, count, skew, st);

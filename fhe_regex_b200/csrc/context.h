@@ -33,10 +33,15 @@ struct fb_ctx {
   fb::c2* d_tabs = nullptr;
   fb::c2* d_wtab = nullptr;    // table of the latency blind rotation (inside the d_tabs allocation)
   fb::c2* d_dtab = nullptr;    // table of the cluster blind rotation (inside the d_tabs allocation)
-  int duo_max = 0;             // batches up to this many PBS take the cluster kernel (off by default; env FB_DUO_MAX)
+  int duo_max = 0;             // batches up to this many PBS take the cluster kernel (off by default; option "cluster_threshold")
   int duo_pairs = 0;           // CTA pairs the device runs at once (cudaOccupancyMaxActiveClusters)
   int quantum = 592;           // SM count x PBS per CTA of the throughput blind rotation
-  int wide_max = 296;          // batches up to this many PBS take the latency kernel (env FB_WIDE_MAX; 0 = never)
+  int wide_max = 296;          // batches up to this many PBS take the latency kernel (option "latency_threshold"; 0 = never)
+  int wide_skew = 200;         // latency kernel: cycles one half of the CTA is held back after the MAC (option "wide_skew")
+  int wide_prefetch = 3;       // latency kernel: GGSW groups fetched before the pre-MAC barrier (option "wide_prefetch")
+  int br_variant = 2;          // throughput blind rotation at 4 PBS per SM: 0 = phase-by-phase body (kernels.cu), 1 = fused body (br_fused.cu), 2 = fused + digits through I2F
+  bool plan_absorb = true;     // false: reference-shaped plan (option "plan_reference_shaped" = 1)
+  bool plan_timing = false;    // planner phase times on stderr (option "plan_timing")
   bool have_key = false;
   // scratch for the batch entry points
   fb_devbuf in, small, out, luts, lut_idx, digits;

@@ -12,12 +12,9 @@
 #include "br_core.cuh"
 #include "kernels.h"
 #include "ptx_sync.cuh"
+#include "br_tmem.cuh"
 
 namespace fb {
-
-__device__ __forceinline__ void bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 
 // ------------------------------------------------------------------------------------------------
 // K7: key conversion.  One CTA (2 warps) per (i, row): the two polynomials of one GLWE row.
@@ -69,43 +66,7 @@ bsk_convert_kernel(const uint64_t* __restrict__ bsk_std, c2* __restrict__ fbsk, 
 // Shared memory: 64 KiB GGSW stage + S * (16 KiB u32 accumulator + 16 KiB transpose plane)
 //                + 12 KiB twiddles + S * 1.5 KiB mod-switched mask + 768 B step flags + mbarrier.
 // ------------------------------------------------------------------------------------------------
-constexpr int kGgswBytes = 4 * kHalfN * (int)sizeof(c2);  // 65536
 
-// ---- tensor memory (TMEM) as thread-private storage of the accumulators ----------------------------
-// TMEM is 128 lanes x 512 32-bit columns per SM; warp w of a CTA may touch lanes 32*(w%4) .. +31 only, and
-// tcgen05.ld/st.32x32b hands thread `lane` consecutive columns of its own lane: exactly a 256 KiB
-// register-file extension.  Each warp owns 64 columns (its 64 u32 coefficients per thread).
-__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr)
-      : "memory");
-  // the registers are valid only after the wait; tying them to it keeps the compiler from using them earlier
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
-                 "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
-               :
-               : "memory");
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
-      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
-      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-constexpr int kTmemCols = 512;
 
 template <int S>
 __global__ void __launch_bounds__(64 * S, 1)

@@ -19,11 +19,14 @@ size_t br_smem_bytes(int S);
 cudaError_t launch_bsk_convert(const uint64_t* bsk_std, c2* fbsk, const c2* tabs, cudaStream_t st);
 cudaError_t launch_blind_rotate(const c2* fbsk, const uint64_t* small, const uint64_t* luts, const uint32_t* lut_idx,
                                 uint64_t* out, const int32_t* out_rows, const c2* tabs, int count, cudaStream_t st);
+// throughput variant with the fused CMUX body, 4 PBS per CTA (br_fused.cu)
+cudaError_t launch_blind_rotate_fused(const c2* fbsk, const uint64_t* small, const uint64_t* luts, const uint32_t* lut_idx, uint64_t* out,
+                                      const int32_t* out_rows, const c2* tabs, int count, int variant, cudaStream_t st);
 // latency variant: one PBS per CTA (br_wide.cu)
 size_t br_wide_table_bytes();
 void br_wide_make_table(c2* host_tab);
 cudaError_t launch_blind_rotate_wide(const c2* fbsk, const uint64_t* small, const uint64_t* luts, const uint32_t* lut_idx,
-                                     uint64_t* out, const int32_t* out_rows, const c2* wtab, int count, cudaStream_t st);
+                                     uint64_t* out, const int32_t* out_rows, const c2* wtab, int count, int skew, int prefetch, cudaStream_t st);
 // cluster variant: one PBS per pair of CTAs (br_duo.cu)
 size_t br_duo_table_bytes();
 void br_duo_make_table(c2* host_tab);

@@ -171,21 +171,27 @@ extern "C" int fb_parse_debug(const char* pattern, char* out, size_t cap) {
   return rc;
 }
 
-extern "C" int fb_plan_stats(const char* pattern, size_t n_chars, fb_match_stats* stats) {
+static PlanOptions options_of(uint32_t flags) {
+  PlanOptions o;
+  o.absorb = (flags & FB_PLAN_REFERENCE_SHAPED) == 0;
+  return o;
+}
+
+extern "C" int fb_plan_stats(const char* pattern, size_t n_chars, uint32_t flags, fb_match_stats* stats) {
   if (!pattern || !stats) return FB_ERR_ARG;
   Plan plan;
   std::string err;
-  int rc = build_plan(pattern, n_chars, 0, 1, plan, err);
+  int rc = build_plan(pattern, n_chars, 0, 1, options_of(flags), plan, err);
   if (rc != FB_OK) return rc;
   *stats = plan.stats;
   return FB_OK;
 }
 
-extern "C" int fb_plan_level_widths(const char* pattern, size_t n_chars, int rank, int world, int32_t* widths, size_t cap) {
+extern "C" int fb_plan_level_widths(const char* pattern, size_t n_chars, int rank, int world, uint32_t flags, int32_t* widths, size_t cap) {
   if (!pattern || (!widths && cap)) return FB_ERR_ARG;
   Plan plan;
   std::string err;
-  int rc = build_plan(pattern, n_chars, rank, world, plan, err);
+  int rc = build_plan(pattern, n_chars, rank, world, options_of(flags), plan, err);
   if (rc != FB_OK) return rc;
   int n = 0;
   for (auto& l : plan.levels) {
@@ -196,18 +202,18 @@ extern "C" int fb_plan_level_widths(const char* pattern, size_t n_chars, int ran
   return n;
 }
 
-extern "C" int fb_plan_eval_plain(const char* pattern, const uint8_t* content, size_t n_chars, int rank, int world, int* result) {
+extern "C" int fb_plan_eval_plain(const char* pattern, const uint8_t* content, size_t n_chars, int rank, int world, uint32_t flags, int* result) {
   if (!pattern || !result || (!content && n_chars)) return FB_ERR_ARG;
   Plan plan;
   std::string err;
-  int rc = build_plan(pattern, n_chars, rank, world, plan, err);
+  int rc = build_plan(pattern, n_chars, rank, world, options_of(flags), plan, err);
   if (rc != FB_OK) return rc;
   return eval_plan_plain(plan, content, 0, result, err);
 }
 
 static int cached_plan(fb_ctx* ctx, const char* pattern, size_t n_chars, int rank, int world, std::shared_ptr<const Plan>& plan) {
   const std::string key = std::string(pattern) + '\n' + std::to_string(n_chars) + '/' + std::to_string(rank) + '/' + std::to_string(world) +
-                          (std::getenv("FB_PLAN_NO_ABSORB") ? "/ref-shaped" : "/absorbed");
+                          (ctx->plan_absorb ? "/absorbed" : "/ref-shaped");
   for (size_t i = 0; i < ctx->plan_cache.size(); i++)
     if (ctx->plan_cache[i].first == key) {
       plan = ctx->plan_cache[i].second;
@@ -216,7 +222,10 @@ static int cached_plan(fb_ctx* ctx, const char* pattern, size_t n_chars, int ran
     }
   auto fresh = std::make_shared<Plan>();
   std::string err;
-  int rc = build_plan(pattern, n_chars, rank, world, *fresh, err);
+  PlanOptions opt;
+  opt.absorb = ctx->plan_absorb;
+  opt.timing = ctx->plan_timing;
+  int rc = build_plan(pattern, n_chars, rank, world, opt, *fresh, err);
   if (rc != FB_OK) return fb_fail(ctx, rc, err);
   plan = fresh;
   ctx->plan_cache.insert(ctx->plan_cache.begin(), std::make_pair(key, plan));

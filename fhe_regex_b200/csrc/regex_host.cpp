@@ -1095,18 +1095,18 @@ uint64_t lut_value(uint32_t lut_id, uint32_t x) {
   return x < 2;
 }
 
-int build_plan(const std::string& pattern, size_t n_chars, int rank, int world, Plan& plan, std::string& err) {
+int build_plan(const std::string& pattern, size_t n_chars, int rank, int world, const PlanOptions& opt, Plan& plan, std::string& err) {
   RegExpr re;
   int rc = parse(pattern, re, err);
   if (rc != FB_OK) return rc;
   if (world < 1 || rank < 0 || rank >= world) { err = "bad rank/world"; return FB_ERR_ARG; }
   try {
-    const bool timing = std::getenv("FB_PLAN_TIMING") != nullptr;
+    const bool timing = opt.timing;
     auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t0 = now();
     Builder B(n_chars);
     std::vector<int32_t> branches;
-    const bool absorb = std::getenv("FB_PLAN_NO_ABSORB") == nullptr;   // reference-shaped plan (every variant evaluated) when set
+    const bool absorb = opt.absorb;   // false: reference-shaped plan (every variant evaluated)
     const bool shard_at_root = absorb && world > 1;                    // see Lowering::shard_operands
     for (size_t i = 0; i < n_chars; i++) {  // engine.rs:15-18
       if (!shard_at_root && (int)(i % (size_t)world) != rank) continue;

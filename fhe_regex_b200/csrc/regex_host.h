@@ -64,7 +64,11 @@ struct Plan {
 
 // Parses, enumerates the variants of every start offset i with i % world == rank, runs the reference's
 // executor bookkeeping and lowers to a plan.  Returns FB_OK / FB_ERR_PARSE / FB_ERR_PANIC.
-int build_plan(const std::string& pattern, size_t n_chars, int rank, int world, Plan& plan, std::string& err);
+struct PlanOptions {
+  bool absorb = true;    // false: reference-shaped plan, every variant the reference enumerates is evaluated
+  bool timing = false;   // print the planner's phase times to stderr
+};
+int build_plan(const std::string& pattern, size_t n_chars, int rank, int world, const PlanOptions& opt, Plan& plan, std::string& err);
 // plan for OR-folding n boolean ciphertexts placed in arena rows 0..n-1
 void build_or_fold_plan(size_t n, Plan& plan);
 

@@ -61,6 +61,20 @@ const char* fb_last_error(const fb_ctx* ctx);
 void* fb_ctx_stream(fb_ctx* ctx);
 int fb_sync(fb_ctx* ctx);
 
+/* ---- options ---------------------------------------------------------------------------------- */
+/* Every knob is per context and set explicitly; the library reads nothing from the environment.
+ *   "latency_threshold"      batches up to this many PBS run the one-PBS-per-CTA blind rotation (default 296, 0 = never)
+ *   "cluster_threshold"      batches up to this many PBS run the one-PBS-per-SM-pair blind rotation (default 0 = never)
+ *   "br_variant"             throughput blind rotation at 4 PBS per SM: 0 phase-by-phase body, 1 fused body, 2 fused body with
+ *                            the digits through the integer-to-double unit (default 2)
+ *   "wide_skew", "wide_prefetch"   tuning of the latency kernel (defaults 200 cycles, 3 groups)
+ *   "plan_reference_shaped"  1: has_match evaluates every variant the reference enumerates (default 0: implied OR
+ *                            operands are absorbed; same decrypted result)
+ *   "plan_timing"            1: planner phase times on stderr
+ * Unknown names and out-of-range values return FB_ERR_ARG. */
+int fb_set_option(fb_ctx* ctx, const char* name, int64_t value);
+int fb_get_option(fb_ctx* ctx, const char* name, int64_t* value);
+
 /* ---- server key ------------------------------------------------------------------------------- */
 /* Replaces `ServerKey::new(&client_key)` / `gen_keys_radix` output being handed to has_match
  * (engine.rs:252, ciphertext.rs:44, mod.rs:16).  Uploads the KSK, converts the BSK to the Fourier
@@ -111,7 +125,7 @@ int fb_has_match(fb_ctx* ctx, const uint64_t* h_content, size_t n_chars, const c
 int fb_has_match_many(fb_ctx* ctx, const uint64_t* h_contents, size_t n_contents, size_t n_chars, const char* pattern,
                       uint64_t* h_out, fb_match_stats* stats);
 /* rank's share of the match: the rank-th of `world` contiguous slices of the final OR's operands after global
- * absorption (reference-shaped plan, FB_PLAN_NO_ABSORB: the variants of start offsets i % world == rank).  The OR
+ * absorption (reference-shaped plan, option "plan_reference_shaped": the variants of start offsets i % world == rank).  The OR
  * of all ranks' results is the match result: all-gather them and fold with fb_or_fold.  stats
  * carries the reference's counters of the whole match and pbs / levels of this rank's plan. */
 int fb_has_match_shard(fb_ctx* ctx, const uint64_t* h_content, size_t n_chars, const char* pattern, int rank, int world,
@@ -122,17 +136,20 @@ int fb_or_fold(fb_ctx* ctx, const uint64_t* h_in, size_t n, uint64_t* h_out);
 /* Parser surface kept from the reference: parse() (parser.rs:146).  Writes the `{:?}` rendering of
  * the RegExpr (parser.rs:87-144) into out (NUL-terminated, truncated to cap).  No GPU needed. */
 int fb_parse_debug(const char* pattern, char* out, size_t cap);
+/* flags of the host-only planner entry points below (a context carries the same choice as option
+ * "plan_reference_shaped") */
+#define FB_PLAN_REFERENCE_SHAPED 1u /* evaluate every variant the reference enumerates: no absorption of implied OR operands */
 /* plaintext dry run of the variant generator + executor bookkeeping (no ciphertexts, no GPU):
  * fills variants / ct_ops / cache_hits / ops_* / pbs / levels / max_level_width. */
-int fb_plan_stats(const char* pattern, size_t n_chars, fb_match_stats* stats);
+int fb_plan_stats(const char* pattern, size_t n_chars, uint32_t flags, fb_match_stats* stats);
 
 /* PBS batch width of every level of the lowered plan (host only): returns the number of levels (>= 0, may
  * exceed cap; only cap entries are written) or a negative error code */
-int fb_plan_level_widths(const char* pattern, size_t n_chars, int rank, int world, int32_t* widths, size_t cap);
+int fb_plan_level_widths(const char* pattern, size_t n_chars, int rank, int world, uint32_t flags, int32_t* widths, size_t cap);
 
 /* plaintext dry run of the lowered circuit on cleartext content bytes (host only, no ciphertexts):
  * result = what decrypt(has_match(..)) would give for this rank's share; used to test the lowering. */
-int fb_plan_eval_plain(const char* pattern, const uint8_t* content, size_t n_chars, int rank, int world, int* result);
+int fb_plan_eval_plain(const char* pattern, const uint8_t* content, size_t n_chars, int rank, int world, uint32_t flags, int* result);
 
 /* ---- timing ----------------------------------------------------------------------------------- */
 typedef struct fb_kernel_stats {

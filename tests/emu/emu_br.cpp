@@ -120,6 +120,102 @@ static void cmux_step(Sample& s, const c2* fbsk, int i, uint32_t a) {
       }
 }
 
+// ---- the fused CMUX body of br_fused.cu, piece by piece in the kernel's order ------------------------------
+template <int B>
+static void emu_mid_block(Sample& s, const c2* fbsk, int i) {
+  for (int w = 0; w < 2; w++)
+    for (int lane = 0; lane < 32; lane++) {
+      Regs& R = s.regs[w][lane];
+      fft32_fwd_s3<B>(R.xr, R.xi);
+      fft32_fwd_s45<2 * B>(R.xr, R.xi);
+      fft32_fwd_s45<2 * B + 1>(R.xr, R.xi);
+    }
+  for (int w = 0; w < 2; w++)
+    for (int t = 0; t < 8; t++) {
+      const int q = 8 * B + t;
+      double pr[32], pi[32];
+      for (int lane = 0; lane < 32; lane++) { pr[lane] = s.regs[w][lane ^ 16].xr[q]; pi[lane] = s.regs[w][lane ^ 16].xi[q]; }
+      for (int lane = 0; lane < 32; lane++) {
+        Regs& R = s.regs[w][lane];
+        const int pp = lane >> 4, k1 = 16 * w + (lane & 15);
+        const int k = k1 + 32 * brev5(q);
+        mac_point2(R.xr[q], R.xi[q], pr[lane], pi[lane], fbsk[fbsk_index(i, pp, pp, k)], fbsk[fbsk_index(i, 1 - pp, pp, k)]);
+      }
+    }
+  for (int w = 0; w < 2; w++)
+    for (int lane = 0; lane < 32; lane++) {
+      Regs& R = s.regs[w][lane];
+      fft32_inv_s12<2 * B>(R.xr, R.xi);
+      fft32_inv_s12<2 * B + 1>(R.xr, R.xi);
+      fft32_inv_s3<B>(R.xr, R.xi);
+    }
+}
+template <int A>
+static void emu_fin_pair(Sample& s, int w, int lane) {
+  Regs& R = s.regs[w][lane];
+  fft32_i2_fin<A>(R.xr, R.xi);
+  uint32_t i0, i1;
+  phaseC_slot<A>(R.xr, R.xi, i0, i1);
+  s.master[w][lane][2 * A] += i0;
+  s.master[w][lane][2 * A + 1] += i1;
+  phaseC_slot<A + 16>(R.xr, R.xi, i0, i1);
+  s.master[w][lane][2 * (A + 16)] += i0;
+  s.master[w][lane][2 * (A + 16) + 1] += i1;
+}
+template <int... As>
+static void emu_fin_all(Sample& s, int w, int lane, fb_iseq<As...>) { (emu_fin_pair<As>(s, w, lane), ...); }
+
+static void cmux_step_fused(Sample& s, const c2* fbsk, int i, uint32_t a) {
+  // the device passes the shared-memory block and the byte offset of the polynomial's copy (a multiple of 8 KiB)
+  const unsigned char* sm = reinterpret_cast<const unsigned char*>(s.shadow.data());
+  for (int w = 0; w < 2; w++)
+    for (int lane = 0; lane < 32; lane++) phaseA_f1(s.regs[w][lane].xr, s.regs[w][lane].xi, sm, (uint32_t)w * 8192u, a, lane);
+  for (int w = 0; w < 2; w++)
+    for (int lane = 0; lane < 32; lane++) fwd_twiddle_inplace(s.regs[w][lane].xr, s.regs[w][lane].xi, g_tab_f, lane);
+  for (int w = 0; w < 2; w++)
+    for (int lane = 0; lane < 32; lane++) col_store_brev(s.regs[w][lane].xr, s.plane.data() + w * kHalfN, lane);
+  for (int w = 0; w < 2; w++)
+    for (int lane = 0; lane < 32; lane++) row_load(s.regs[w][lane].xr, s.plane.data() + (lane >> 4) * kHalfN, 16 * w + (lane & 15));
+  for (int w = 0; w < 2; w++)
+    for (int lane = 0; lane < 32; lane++) col_store_brev(s.regs[w][lane].xi, s.plane.data() + w * kHalfN, lane);
+  for (int w = 0; w < 2; w++)
+    for (int lane = 0; lane < 32; lane++) row_load(s.regs[w][lane].xi, s.plane.data() + (lane >> 4) * kHalfN, 16 * w + (lane & 15));
+  for (int w = 0; w < 2; w++)
+    for (int lane = 0; lane < 32; lane++) fft32_fwd_s12(s.regs[w][lane].xr, s.regs[w][lane].xi);
+  emu_mid_block<0>(s, fbsk, i);
+  emu_mid_block<1>(s, fbsk, i);
+  emu_mid_block<2>(s, fbsk, i);
+  emu_mid_block<3>(s, fbsk, i);
+  for (int w = 0; w < 2; w++)
+    for (int lane = 0; lane < 32; lane++) {
+      Regs& R = s.regs[w][lane];
+      fft32_inv_s45(R.xr, R.xi);
+      inv_twiddle_inplace(R.xr, R.xi, g_tab_i, 16 * w + (lane & 15));
+    }
+  for (int w = 0; w < 2; w++)
+    for (int lane = 0; lane < 32; lane++) row_store(s.regs[w][lane].xr, s.plane.data() + (lane >> 4) * kHalfN, 16 * w + (lane & 15));
+  for (int w = 0; w < 2; w++)
+    for (int lane = 0; lane < 32; lane++) col_load_brev(s.regs[w][lane].xr, s.plane.data() + w * kHalfN, lane);
+  for (int w = 0; w < 2; w++)
+    for (int lane = 0; lane < 32; lane++) row_store(s.regs[w][lane].xi, s.plane.data() + (lane >> 4) * kHalfN, 16 * w + (lane & 15));
+  for (int w = 0; w < 2; w++)
+    for (int lane = 0; lane < 32; lane++) col_load_brev(s.regs[w][lane].xi, s.plane.data() + w * kHalfN, lane);
+  for (int w = 0; w < 2; w++)
+    for (int lane = 0; lane < 32; lane++) {
+      fft32_i2_head(s.regs[w][lane].xr, s.regs[w][lane].xi);
+      emu_fin_all(s, w, lane, fb_make_iseq<16>{});
+    }
+  for (int w = 0; w < 2; w++)
+    for (int lane = 0; lane < 32; lane++)
+      for (int r = 0; r < 32; r++) {
+        s.shadow[w * kN + 32 * r + lane] = s.master[w][lane][2 * r];
+        s.shadow[w * kN + 32 * r + lane + 1024] = s.master[w][lane][2 * r + 1];
+      }
+}
+
+static bool g_fused = false;
+extern "C" void emu_set_fused(int on) { g_fused = on != 0; }
+
 // small[743], lut[2048] -> acc[2][2048]; max_steps < 0 means all 742
 extern "C" void emu_blind_rotate(const c2* fbsk, const uint64_t* small, const uint64_t* lut, uint64_t* acc_out, int max_steps) {
   tabs();
@@ -138,7 +234,8 @@ extern "C" void emu_blind_rotate(const c2* fbsk, const uint64_t* small, const ui
   for (int i = 0; i < steps; i++) {
     const uint32_t a = modswitch(small[i]) & 4095u;
     if (small[i] == 0 || a == 0) continue;
-    cmux_step(s, fbsk, i, a);
+    if (g_fused) cmux_step_fused(s, fbsk, i, a);
+    else cmux_step(s, fbsk, i, a);
   }
   for (int w = 0; w < 2; w++)
     for (int lane = 0; lane < 32; lane++)

@@ -69,6 +69,36 @@ def test_emulated_blind_rotate_decrypts_like_the_oracle(emu, emu_fbsk, client_ke
         assert np.abs(err).max() < 4e-4, err
 
 
+def test_emulated_fused_body_matches_phase_by_phase_body(emu, emu_fbsk, client_key, server_key):
+    """br_fused.cu re-orders the per-thread program (digits interleaved with pass 1, MAC block by block between the
+    transforms, untwist folded into the last butterflies, three-FMA torus rounding): same function.  After ONE CMUX
+    step the accumulators agree to f64 rounding (values of ~2^27 carry ~2^-25 of absolute error = ~2^7 units of 2^-32);
+    later steps are not comparable bit by bit (a digit that rounds the other way adds a whole key coefficient -- noise
+    to the decryption, not to the ciphertext bits), so the full rotation is compared by decryption and error bound."""
+    cts = tfhe.encrypt_batch(client_key, np.array([7], dtype=np.int64), seed=78)
+    small = tfhe.keyswitch(server_key, cts)[0]
+    lut = tfhe.make_lut(lambda x: (x * 7 + 2) % 16)
+    accs = []
+    for fused in (0, 1):
+        emu.emu_set_fused(fused)
+        acc = np.zeros(2 * 2048, dtype=np.uint64)
+        emu.emu_blind_rotate(_p(emu_fbsk), _p(small), _p(lut), _p(acc), 1)
+        accs.append(acc)
+    emu.emu_set_fused(0)
+    d = (accs[0] >> np.uint64(32)).astype(np.int64) - (accs[1] >> np.uint64(32)).astype(np.int64)
+    d = (d + (1 << 31)) % (1 << 32) - (1 << 31)
+    assert 0 < np.abs(accs[0]).max() and np.abs(d).max() <= 512, np.abs(d).max()
+    # and the full rotation decrypts correctly through the fused body
+    emu.emu_set_fused(1)
+    acc = np.zeros(2 * 2048, dtype=np.uint64)
+    emu.emu_blind_rotate(_p(emu_fbsk), _p(small), _p(lut), _p(acc), -1)
+    emu.emu_set_fused(0)
+    out = tfhe.sample_extract(acc)
+    assert tfhe.decrypt_shortint(client_key, out) == (7 * 7 + 2) % 16
+    err = tfhe.torus_err(tfhe.phase_batch(client_key.big, out[None]), np.array([((7 * 7 + 2) % 16) << 59], dtype=np.uint64))
+    assert np.abs(err).max() < 4e-4, err
+
+
 def test_emulated_trivial_input_is_exact(emu, emu_fbsk, server_key):
     lut = tfhe.make_lut(lambda x: (5 * x) % 16)
     small = np.zeros(743, dtype=np.uint64)

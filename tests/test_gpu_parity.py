@@ -284,7 +284,7 @@ def test_has_match_64_char_configs(fck, gpu_key):
         assert fck.decrypt(res) == rp.has_match(content, pattern), (content, pattern)
 
 
-def test_has_match_256_char_config5_both_plans(fck, gpu_key, monkeypatch):
+def test_has_match_256_char_config5_both_plans(fck, gpu_key):
     # BASELINE config 5 at full size: 65 025 variants; the reference-shaped plan evaluates all of them (~76k PBS),
     # the default plan absorbs implied variants (~1.6k PBS); both must decrypt to the reference's result
     rng = np.random.default_rng(12)
@@ -295,8 +295,11 @@ def test_has_match_256_char_config5_both_plans(fck, gpu_key, monkeypatch):
         exp = rp.has_match(content, "/a+b?c/")
         res, st = fb.has_match(gpu_key, ct, "/a+b?c/", return_stats=True)
         assert fck.decrypt(res) == exp and st["pbs"] < 3000 and st["variants"] == 65025
-    monkeypatch.setenv("FB_PLAN_NO_ABSORB", "1")
-    res, st = fb.has_match(gpu_key, fb.encrypt_str(fck, hit, seed=13), "/a+b?c/", return_stats=True)
+    prev = gpu_key.set_option("plan_reference_shaped", 1)
+    try:
+        res, st = fb.has_match(gpu_key, fb.encrypt_str(fck, hit, seed=13), "/a+b?c/", return_stats=True)
+    finally:
+        gpu_key.set_option("plan_reference_shaped", prev)
     assert fck.decrypt(res) == 1 and st["pbs"] > 60000 and (st["ct_ops"], st["cache_hits"]) == (195583, 11118596)
 
 

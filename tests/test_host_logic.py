@@ -95,29 +95,25 @@ def test_counters_match_reference_bookkeeping(row):
                [by.get(k, 0) for k in ("eq", "gt", "le", "and", "or", "not")]
 
 
-def test_config5_plan_shape(monkeypatch):
+def test_config5_plan_shape():
     # reference-shaped plan (every variant evaluated): ~75k PBS in <= 16 dependent levels
-    monkeypatch.setenv("FB_PLAN_NO_ABSORB", "1")
-    st = fb.plan_stats("/a+b?c/", 256)
+    st = fb.plan_stats("/a+b?c/", 256, reference_shaped=True)
     assert 60000 < st["pbs"] < 80000 and st["levels"] <= 16 and st["max_level_width"] > 10000
     ref_counters = (st["variants"], st["ct_ops"], st["cache_hits"])
     # default plan: OR operands implied by another operand are absorbed (x | (x & y) = x); the reference's
     # bookkeeping counters are unaffected, the PBS count collapses from O(n^2) to O(n)
-    monkeypatch.delenv("FB_PLAN_NO_ABSORB")
     st = fb.plan_stats("/a+b?c/", 256)
     assert st["pbs"] < 3000 and st["levels"] <= 8
     assert (st["variants"], st["ct_ops"], st["cache_hits"]) == ref_counters == (65025, 195583, 11118596)
 
 
-def test_absorbed_and_reference_shaped_plans_agree(monkeypatch):
+def test_absorbed_and_reference_shaped_plans_agree():
     rnd = random.Random(11)
     for it in range(300):
         pat = rnd.choice(PATTERNS)
         max_n = 8 if "|" in pat and ("+" in pat or "*" in pat) else 20
         content = "".join(rnd.choice("abcxyAB.") for _ in range(rnd.randint(0, max_n)))
-        monkeypatch.setenv("FB_PLAN_NO_ABSORB", "1")
-        a = fb.plan_eval_plain(pat, content)
-        monkeypatch.delenv("FB_PLAN_NO_ABSORB")
+        a = fb.plan_eval_plain(pat, content, reference_shaped=True)
         assert fb.plan_eval_plain(pat, content) == a == rp.has_match(content, pat), (pat, content)
 
 

@@ -138,6 +138,10 @@ class Emitter:
         for p in range(32):
             assert abs(float(self.mag[p]) - 1.0) < 1e-15 and self.sr[p] == 1 and self.si[p] == 1, (p, self.mag[p], self.sr[p], self.si[p])
 
+    def mark(self):
+        """index of the next emitted line (pieces of a routine are slices of self.lines)"""
+        return len(self.lines)
+
 
 def gen_dit(sign, slot_of_pos, twist):
     """DIT network over positions 0..31 (position p holds input x[brev5(p)]); array slot = slot_of_pos(p).
@@ -159,6 +163,136 @@ def gen_dit(sign, slot_of_pos, twist):
         half *= 2
     E.finish()
     return E
+
+
+
+def dit_stages(sign, slot_of_pos):
+    """butterflies of the 32-point DIT network as {stage: [(a_slot, b_slot, c, s)]}, stage = 1..5"""
+    st = {}
+    half, stage = 1, 1
+    while half <= 16:
+        ops = []
+        for g in range(0, 32, 2 * half):
+            for j in range(half):
+                c, s = cs_frac(Fraction(sign * j, 2 * half))
+                ops.append((slot_of_pos(g + j), slot_of_pos(g + j + half), c, s))
+        st[stage] = ops
+        half *= 2
+        stage += 1
+    return st
+
+
+def emit_ops(E, ops):
+    for a, b, c, s in ops:
+        E.rotate(b, c, s)
+        E.butterfly(a, b)
+
+
+def gen_mid_pieces():
+    """Forward pass 2 and inverse pass 1 cut into pieces so that the Fourier MAC can run block by block between
+    them: the last three forward stages and the first three inverse stages stay inside aligned blocks of 8 slots
+    (the last / first two inside blocks of 4).  Returns ([(name, lines)], slots)."""
+    pieces = []
+    F = Emitter()
+    fs = dit_stages(-1, brev5)
+    m = F.mark()
+    emit_ops(F, fs[1] + fs[2])
+    pieces.append(("fft32_fwd_s12", F.lines[m:]))
+    for b in range(4):
+        m = F.mark()
+        emit_ops(F, [o for o in fs[3] if o[0] // 8 == b])
+        assert all(o[1] // 8 == b for o in fs[3] if o[0] // 8 == b)
+        pieces.append((f"fft32_fwd_s3_b{b}", F.lines[m:]))
+        for q in (2 * b, 2 * b + 1):
+            m = F.mark()
+            sel = [o for o in fs[4] + fs[5] if o[0] // 4 == q]
+            assert all(o[1] // 4 == q for o in sel) and len(sel) == 4
+            emit_ops(F, sel)
+            pieces.append((f"fft32_fwd_s45_q{q}", F.lines[m:]))
+    F.finish()
+    I = Emitter()
+    isg = dit_stages(+1, lambda p: p)
+    for b in range(4):
+        for q in (2 * b, 2 * b + 1):
+            m = I.mark()
+            sel = [o for o in isg[1] + isg[2] if o[0] // 4 == q]
+            assert all(o[1] // 4 == q for o in sel) and len(sel) == 4
+            emit_ops(I, sel)
+            pieces.append((f"fft32_inv_s12_q{q}", I.lines[m:]))
+        m = I.mark()
+        sel = [o for o in isg[3] if o[0] // 8 == b]
+        assert all(o[1] // 8 == b for o in sel)
+        emit_ops(I, sel)
+        pieces.append((f"fft32_inv_s3_b{b}", I.lines[m:]))
+    m = I.mark()
+    emit_ops(I, isg[4] + isg[5])
+    pieces.append(("fft32_inv_s45", I.lines[m:]))
+    I.finish()
+    return pieces, F.slots, I.slots
+
+
+F1_ORDER = [brev5(n) for n in range(32)]   # slot whose digits are produced n-th: 0, 16, 8, 24, 4, ...
+
+
+def gen_f1_progressive():
+    """Forward pass 1 (with the input twist) as 32 steps: step n runs everything that becomes computable once the
+    digits of slot F1_ORDER[n] are there, so that the decomposition (integer / shared-memory work) and the
+    butterflies (FP64) interleave in program order."""
+    E = Emitter()
+    fs = dit_stages(-1, brev5)
+    level = [0] * 32      # stages completed per slot
+    loaded = [False] * 32
+    todo = {s: list(fs[s]) for s in fs}
+    steps = []
+    for n in range(32):
+        r = F1_ORDER[n]
+        m = E.mark()
+        c, s = cs_frac(Fraction(r, 128))
+        E.rotate(r, c, s)
+        loaded[r] = True
+        progress = True
+        while progress:
+            progress = False
+            for st in range(1, 6):
+                rest = []
+                for op in todo[st]:
+                    a, b = op[0], op[1]
+                    if loaded[a] and loaded[b] and level[a] == st - 1 and level[b] == st - 1:
+                        emit_ops(E, [op])
+                        level[a] = level[b] = st
+                        progress = True
+                    else:
+                        rest.append(op)
+                todo[st] = rest
+        steps.append(E.lines[m:])
+    assert all(not todo[s] for s in todo)
+    E.finish()
+    return steps, E.slots
+
+
+def gen_i2_final():
+    """Inverse pass 2 with the output untwist exp(-i*pi*r/64) folded in: stages 1-4 in one piece, then the 16
+    butterflies of the last stage one by one, each followed by the untwist of its two outputs in tangent form.
+    The real factor of the untwist stays pending: slot r's true value is kre[r] * xr[r] + i * kim[r] * xi[r];
+    phase C folds kre / kim (and the 1/1024 of the inverse transform) into the FMAs of its torus rounding."""
+    E = Emitter()
+    isg = dit_stages(+1, lambda p: p)
+    m = E.mark()
+    emit_ops(E, isg[1] + isg[2] + isg[3] + isg[4])
+    head = E.lines[m:]
+    fins = []
+    for op in isg[5]:
+        a, b = op[0], op[1]
+        assert b == a + 16
+        m = E.mark()
+        emit_ops(E, [op])
+        for r in (a, b):
+            c, s = cs_frac(Fraction(-r, 128))
+            E.rotate(r, c, s)
+        fins.append((a, E.lines[m:]))
+    kre = [float(E.sr[r] * E.mag[r]) for r in range(32)]
+    kim = [float(E.si[r] * E.mag[r]) for r in range(32)]
+    return head, fins, kre, kim, E.slots
 
 
 def replay(lines, xr, xi):
@@ -226,6 +360,108 @@ def main():
         body += ["  " + l for l in E.lines]
         body.append("}")
         body.append("")
+    # ---- pieces for the fused CMUX body (kernels.cu, variant "fused") ---------------------------------------
+    def fn(name, lines, comment=None):
+        if comment:
+            body.append("// " + comment)
+        body.append(f"FB_HD void {name}(double (&xr)[32], double (&xi)[32]) {{")
+        body.extend("  " + l for l in lines)
+        body.append("}")
+
+    def dft(x, sign):
+        return np.array([sum(x[n] * np.exp(sign * 2j * np.pi * n * k / 32) for n in range(32)) for k in range(32)])
+
+    rng = np.random.default_rng(2)
+    pieces, fslots, islots = gen_mid_pieces()
+    # replay in the kernel's order: s12, then per block of 8 (s3, s45 x2 | MAC omitted | inv s12 x2, inv s3), inv s45
+    x = rng.standard_normal(32) + 1j * rng.standard_normal(32)
+    xr, xi = x.real.copy(), x.imag.copy()
+    pd = dict(pieces)
+    order_f = ["fft32_fwd_s12"] + [n for b in range(4) for n in (f"fft32_fwd_s3_b{b}", f"fft32_fwd_s45_q{2*b}", f"fft32_fwd_s45_q{2*b+1}")]
+    for n in order_f:
+        replay(pd[n], xr, xi)
+    ref = dft(x, -1)
+    errf = max(abs((xr[brev5(k)] + 1j * xi[brev5(k)]) - ref[k]) for k in range(32))
+    y = rng.standard_normal(32) + 1j * rng.standard_normal(32)
+    yr, yi = np.zeros(32), np.zeros(32)
+    for q in range(32):
+        yr[q], yi[q] = y[brev5(q)].real, y[brev5(q)].imag
+    order_i = [n for b in range(4) for n in (f"fft32_inv_s12_q{2*b}", f"fft32_inv_s12_q{2*b+1}", f"fft32_inv_s3_b{b}")] + ["fft32_inv_s45"]
+    for n in order_i:
+        replay(pd[n], yr, yi)
+    refi = dft(y, +1)
+    erri = max(abs((yr[k] + 1j * yi[k]) - refi[k]) for k in range(32))
+    assert errf < 1e-12 and erri < 1e-12, (errf, erri)
+    print(f"mid pieces: fwd {fslots} + inv {islots} FP64 slots, replay max err {errf:.2e} / {erri:.2e}")
+    body.append("// ---- forward pass 2 / inverse pass 1 in pieces: the Fourier MAC runs block by block between them")
+    for name, lines in pieces:
+        fn(name, lines)
+    for stem, count in (("fft32_fwd_s3_b", 4), ("fft32_fwd_s45_q", 8), ("fft32_inv_s12_q", 8), ("fft32_inv_s3_b", 4)):
+        body.append(f"template <int I> FB_HD void {stem[:-2]}(double (&xr)[32], double (&xi)[32]) {{")
+        for i in range(count):
+            body.append(f"  if constexpr (I == {i}) {stem}{i}(xr, xi);")
+        body.append("}")
+    body.append("")
+
+    steps, f1slots = gen_f1_progressive()
+    x = rng.standard_normal(32) + 1j * rng.standard_normal(32)
+    xr, xi = np.zeros(32), np.zeros(32)
+    for n in range(32):
+        r = F1_ORDER[n]
+        xr[r], xi[r] = x[r].real, x[r].imag      # "digits of slot r arrive"
+        replay(steps[n], xr, xi)
+    ref = dft(x * np.exp(1j * np.pi * np.arange(32) / 64), -1)
+    err1 = max(abs((xr[brev5(k)] + 1j * xi[brev5(k)]) - ref[k]) for k in range(32))
+    assert err1 < 1e-12, err1
+    print(f"f1 progressive: {f1slots} FP64 slots, replay max err {err1:.2e}")
+    body.append("// ---- forward pass 1 with the input twist, progressive: step n runs what becomes computable once slot")
+    body.append("// fb_f1_order(n) holds its digits (decomposition and butterflies interleave in program order)")
+    body.append("FB_HD constexpr int fb_f1_order(int n) {")
+    body.append("  switch (n) {")
+    for n in range(32):
+        body.append(f"    case {n}: return {F1_ORDER[n]};")
+    body.append("  }")
+    body.append("  return 0;")
+    body.append("}")
+    for n in range(32):
+        fn(f"fft32_f1_step{n}", steps[n])
+    body.append("template <int N> FB_HD void fft32_f1_step(double (&xr)[32], double (&xi)[32]) {")
+    for n in range(32):
+        body.append(f"  if constexpr (N == {n}) fft32_f1_step{n}(xr, xi);")
+    body.append("}")
+    body.append("")
+
+    head, fins, kre, kim, i2slots = gen_i2_final()
+    y = rng.standard_normal(32) + 1j * rng.standard_normal(32)
+    yr, yi = np.zeros(32), np.zeros(32)
+    for q in range(32):
+        yr[q], yi[q] = y[brev5(q)].real, y[brev5(q)].imag
+    replay(head, yr, yi)
+    for a, lines in fins:
+        replay(lines, yr, yi)
+    refi = dft(y, +1) * np.exp(-1j * np.pi * np.arange(32) / 64)
+    err2 = max(abs((kre[k] * yr[k] + 1j * kim[k] * yi[k]) - refi[k]) for k in range(32))
+    assert err2 < 1e-12, err2
+    print(f"i2 final: {i2slots} FP64 slots (untwist folded), replay max err {err2:.2e}")
+    body.append("// ---- inverse pass 2 with the output untwist folded in: head = stages 1-4, then the last stage butterfly by")
+    body.append("// butterfly (slots a, a+16); true value of slot r = fb_i2_kre(r) * xr[r] + i * fb_i2_kim(r) * xi[r]")
+    fn("fft32_i2_head", head)
+    for a, lines in fins:
+        fn(f"fft32_i2_fin{a}", lines)
+    body.append("template <int A> FB_HD void fft32_i2_fin(double (&xr)[32], double (&xi)[32]) {")
+    for a, _ in fins:
+        body.append(f"  if constexpr (A == {a}) fft32_i2_fin{a}(xr, xi);")
+    body.append("}")
+    for nm, tab in (("kre", kre), ("kim", kim)):
+        body.append(f"FB_HD constexpr double fb_i2_{nm}(int r) {{")
+        body.append("  switch (r) {")
+        for r in range(32):
+            body.append(f"    case {r}: return {lit(tab[r])};")
+        body.append("  }")
+        body.append("  return 0.0;")
+        body.append("}")
+    body.append("")
+
     out.append("// butterfly constants (tangents and magnitude ratios); device code reads them from the constant bank")
     out.append("#define FB_KTAB_INIT { " + ", ".join(lit(k) for k in KTAB) + " }")
     out.append("#if defined(__CUDACC__)")

@@ -1,0 +1,40 @@
+#!/usr/bin/env python3
+"""PBS/s of the throughput blind rotation per option setting: variant_probe.py [B ...] (default 592 28416).
+Every run decrypts a sample of the outputs."""
+import json, os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import fhe_regex_b200 as fb  # noqa: E402
+
+def main():
+    ck = fb.ClientKey.load(os.path.join(ROOT, "tests", "golden", "client_key"))
+    ksk, bsk = fb.keygen_server_raw(ck, seed=0)
+    sk = fb.ServerKey(ksk, bsk)
+    sk.timing(True)
+    sizes = [int(a) for a in sys.argv[1:] if a.isdigit()] or [592, 28416]
+    variants = [int(v) for v in os.environ.get("PROBE_VARIANTS", "0,1").split(",")]
+    f = lambda x: (3 * x + 1) % 16
+    lut = fb.make_lut(f)
+    for B in sizes:
+        msgs = np.arange(B) % 16
+        cts = ck.encrypt_blocks(msgs[: min(B, 256)], seed=3)
+        cts = np.ascontiguousarray(np.tile(cts, ((B + cts.shape[0] - 1) // cts.shape[0], 1))[:B])
+        idx = np.zeros(B, dtype=np.uint32)
+        for v in variants:
+            sk.set_option("br_variant", v)
+            sk.pbs(cts, lut[None], idx)
+            best = None
+            for rep in range(3):
+                sk.kernel_stats(reset=True)
+                res = sk.pbs(cts, lut[None], idx)
+                st = sk.kernel_stats(reset=True)
+                best = st["br_ms"] if best is None else min(best, st["br_ms"])
+            pick = np.linspace(0, B - 1, num=min(B, 96), dtype=np.int64)
+            ok = all(ck.decrypt_block(res[i]) == f(int(msgs[i])) for i in pick)
+            print(json.dumps({"B": B, "variant": v, "br_ms": best, "ks_ms": st["ks_ms"], "pbs_per_s": B / ((best + st["ks_ms"]) / 1e3),
+                              "br_tflops": B * 194510848 / (best / 1e3) / 1e12, "ok": ok}), flush=True)
+    sk.close()
+
+if __name__ == "__main__":
+    main()
