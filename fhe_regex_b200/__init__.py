@@ -88,6 +88,18 @@ def lib():
     L.fb_plan_stats.argtypes = [C.c_char_p, sz, C.c_uint32, C.POINTER(MatchStats)]
     L.fb_plan_level_widths.argtypes = [C.c_char_p, sz, C.c_int, C.c_int, C.c_uint32, vp, sz]
     L.fb_plan_eval_plain.argtypes = [C.c_char_p, vp, sz, C.c_int, C.c_int, C.c_uint32, C.POINTER(C.c_int)]
+    L.fb_load_server_key_fourier.argtypes = [vp, vp, vp]
+    L.fb_load_server_key_bincode.argtypes = [vp, vp, sz]
+    L.fb_server_key_bincode_size.restype = sz
+    L.fb_server_key_bincode_size.argtypes = []
+    L.fb_server_key_from_bincode.argtypes = [vp, sz, vp, vp]
+    L.fb_server_key_to_bincode.argtypes = [vp, vp, vp, sz, C.POINTER(sz)]
+    L.fb_radix_bincode_size.restype = sz
+    L.fb_radix_bincode_size.argtypes = []
+    L.fb_radix_from_bincode.argtypes = [vp, sz, vp, vp]
+    L.fb_radix_to_bincode.argtypes = [vp, vp, vp, sz, C.POINTER(sz)]
+    L.fb_string_ciphertext_from_bincode.argtypes = [vp, sz, vp, sz, C.POINTER(sz)]
+    L.fb_string_ciphertext_to_bincode.argtypes = [vp, sz, vp, sz, C.POINTER(sz)]
     L.fb_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     L.fb_get_option.argtypes = [vp, C.c_char_p, C.POINTER(C.c_int64)]
     L.fb_kernel_stats_reset.argtypes = [vp]
@@ -168,6 +180,76 @@ def plan_eval_plain(pattern: str, content: str, rank: int = 0, world: int = 1, r
     if rc != FB_OK:
         _raise(rc, "plan dry run failed for %r" % pattern)
     return res.value
+
+
+# ---- tfhe-rs 0.2.0 wire formats (fhe_regex_b200/csrc/wire.cpp) ---------------------------------------------------
+def server_key_to_bincode(ksk: np.ndarray, fourier_bsk: np.ndarray) -> bytes:
+    """bincode::serialize(&integer::ServerKey) from the keyswitch container and the Fourier key in serialized order"""
+    ksk = np.ascontiguousarray(ksk, dtype=np.uint64)
+    f = np.ascontiguousarray(fourier_bsk, dtype=np.float64)
+    assert ksk.size == KSK_WORDS and f.size == 742 * 4 * 1024 * 2
+    out = np.empty(lib().fb_server_key_bincode_size(), dtype=np.uint8)
+    n = C.c_size_t(0)
+    rc = lib().fb_server_key_to_bincode(_p(ksk), _p(f), _p(out), out.size, C.byref(n))
+    if rc != FB_OK or n.value != out.size:
+        _raise(rc, "server key serialization failed")
+    return out.tobytes()
+
+
+def server_key_from_bincode(blob: bytes):
+    buf = np.frombuffer(blob, dtype=np.uint8)
+    ksk = np.empty(KSK_WORDS, dtype=np.uint64)
+    f = np.empty((742, 2, 2, 1024, 2), dtype=np.float64)
+    rc = lib().fb_server_key_from_bincode(_p(buf), buf.size, _p(ksk), _p(f))
+    if rc != FB_OK:
+        _raise(rc, "not a bincode tfhe::integer::ServerKey of PARAM_MESSAGE_2_CARRY_2")
+    return ksk.reshape(2048, 5, 743), f
+
+
+def string_ciphertext_to_bincode(content: np.ndarray) -> bytes:
+    """bincode::serialize(&Vec<RadixCiphertext>) = StringCiphertext (ciphertext.rs:6) from [n][4][2049] words"""
+    content = np.ascontiguousarray(content, dtype=np.uint64).reshape(-1, 4, BIG)
+    n = C.c_size_t(0)
+    lib().fb_string_ciphertext_to_bincode(_p(content), content.shape[0], None, 0, C.byref(n))
+    out = np.empty(n.value, dtype=np.uint8)
+    rc = lib().fb_string_ciphertext_to_bincode(_p(content), content.shape[0], _p(out), out.size, C.byref(n))
+    if rc != FB_OK:
+        _raise(rc, "ciphertext serialization failed")
+    return out.tobytes()
+
+
+def string_ciphertext_from_bincode(blob: bytes) -> np.ndarray:
+    buf = np.frombuffer(blob, dtype=np.uint8)
+    n = C.c_size_t(0)
+    rc = lib().fb_string_ciphertext_from_bincode(_p(buf), buf.size, None, 0, C.byref(n))
+    if rc != FB_OK:
+        _raise(rc, "not a bincode Vec<RadixCiphertext>")
+    out = np.empty((n.value, 4, BIG), dtype=np.uint64)
+    rc = lib().fb_string_ciphertext_from_bincode(_p(buf), buf.size, _p(out), n.value, C.byref(n))
+    if rc != FB_OK:
+        _raise(rc, "not a bincode Vec<RadixCiphertext>")
+    return out
+
+
+def radix_to_bincode(ct: np.ndarray, degrees=None) -> bytes:
+    ct = np.ascontiguousarray(ct, dtype=np.uint64).reshape(4, BIG)
+    out = np.empty(lib().fb_radix_bincode_size(), dtype=np.uint8)
+    n = C.c_size_t(0)
+    deg = None if degrees is None else np.ascontiguousarray(degrees, dtype=np.uint64)
+    rc = lib().fb_radix_to_bincode(_p(ct), None if deg is None else _p(deg), _p(out), out.size, C.byref(n))
+    if rc != FB_OK:
+        _raise(rc, "ciphertext serialization failed")
+    return out.tobytes()
+
+
+def radix_from_bincode(blob: bytes):
+    buf = np.frombuffer(blob, dtype=np.uint8)
+    ct = np.empty((4, BIG), dtype=np.uint64)
+    deg = np.empty(4, dtype=np.uint64)
+    rc = lib().fb_radix_from_bincode(_p(buf), buf.size, _p(ct), _p(deg))
+    if rc != FB_OK:
+        _raise(rc, "not a bincode RadixCiphertext")
+    return ct, deg
 
 
 def make_lut(f) -> np.ndarray:
@@ -257,7 +339,11 @@ def keygen_server_raw(client_key: ClientKey, seed: int = 0):
 class ServerKey:
     """The server key resident on one B200 (KSK + Fourier BSK in HBM) plus the evaluation context."""
 
-    def __init__(self, ksk: np.ndarray, bsk_std: np.ndarray, device: int = 0):
+    def __init__(self, ksk: np.ndarray = None, bsk_std: np.ndarray = None, device: int = 0, *, fourier_bsk: np.ndarray = None,
+                 bincode: bytes = None):
+        """ksk + bsk_std: the two tfhe-rs containers in the standard domain (fb_load_server_key_raw);
+        ksk + fourier_bsk: the Fourier key in tfhe-rs's serialized order (fb_load_server_key_fourier);
+        bincode: a serialized tfhe::integer::ServerKey (fb_load_server_key_bincode)."""
         L = lib()
         self._h = C.c_void_p()
         rc = L.fb_ctx_create(C.byref(self._h), device)
@@ -265,9 +351,19 @@ class ServerKey:
             msg = L.fb_last_error(None).decode()
             self._h = None
             raise FbError(rc, msg)
+        if bincode is not None:
+            buf = np.frombuffer(bincode, dtype=np.uint8)
+            self._check(L.fb_load_server_key_bincode(self._h, _p(buf), buf.size))
+            return
         ksk = np.ascontiguousarray(ksk, dtype=np.uint64)
+        assert ksk.size == KSK_WORDS
+        if fourier_bsk is not None:
+            f = np.ascontiguousarray(fourier_bsk, dtype=np.float64)
+            assert f.size == 742 * 4 * 1024 * 2
+            self._check(L.fb_load_server_key_fourier(self._h, _p(ksk), _p(f)))
+            return
         bsk_std = np.ascontiguousarray(bsk_std, dtype=np.uint64)
-        assert ksk.size == KSK_WORDS and bsk_std.size == BSK_WORDS
+        assert bsk_std.size == BSK_WORDS
         self._check(L.fb_load_server_key_raw(self._h, _p(ksk), _p(bsk_std)))
 
     def _check(self, rc):

@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <vector>
 #include "context.h"
 
 using fb::c2;
@@ -105,19 +106,49 @@ extern "C" int fb_sync(fb_ctx* ctx) {
   return FB_OK;
 }
 
-extern "C" int fb_load_server_key_raw(fb_ctx* ctx, const uint64_t* h_ksk, const uint64_t* h_bsk_std) {
-  if (!ctx || !h_ksk || !h_bsk_std) return fb_fail(ctx, FB_ERR_ARG, "null argument");
-  FB_CUDA(ctx, cudaSetDevice(ctx->device));
+// keyswitch key: upload the u64 container, keep only its byte planes resident
+static int upload_ksk(fb_ctx* ctx, const uint64_t* h_ksk) {
   if (!ctx->d_fbsk) FB_CUDA(ctx, cudaMalloc(&ctx->d_fbsk, (size_t)fb::kLweN * 4 * fb::kHalfN * sizeof(c2)));
   if (!ctx->d_kb) FB_CUDA(ctx, cudaMalloc(&ctx->d_kb, fb::ks_key_bytes()));
   uint64_t* d_ksk = nullptr;  // staging copy of the u64 key; only its byte planes stay resident
   FB_CUDA(ctx, cudaMalloc(&d_ksk, FB_KSK_WORDS * sizeof(uint64_t)));
+  cudaError_t e = cudaMemcpyAsync(d_ksk, h_ksk, FB_KSK_WORDS * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = fb::launch_ksk_bytes(d_ksk, ctx->d_kb, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_ksk);
+  if (e != cudaSuccess) return fb_cuda_fail(ctx, e, "keyswitch key upload / byte-plane split");
+  return FB_OK;
+}
+
+// The bootstrapping key as a tfhe-rs 0.2.0 ServerKey holds it: Fourier domain only.  h_fbsk is the key in the serialized
+// (plan-independent, natural frequency) order -- see wire.cpp -- which is this library's resident layout: a copy.
+extern "C" int fb_load_server_key_fourier(fb_ctx* ctx, const uint64_t* h_ksk, const double* h_fbsk) {
+  if (!ctx || !h_ksk || !h_fbsk) return fb_fail(ctx, FB_ERR_ARG, "null argument");
+  FB_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = upload_ksk(ctx, h_ksk);
+  if (rc != FB_OK) return rc;
+  FB_CUDA(ctx, cudaMemcpyAsync(ctx->d_fbsk, h_fbsk, (size_t)fb::kLweN * 4 * fb::kHalfN * sizeof(c2), cudaMemcpyHostToDevice, ctx->stream));
+  FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->have_key = true;
+  return FB_OK;
+}
+
+// bincode of tfhe::integer::ServerKey (wire.cpp): what the reference's keygen produces (engine.rs:252, ciphertext.rs:44)
+extern "C" int fb_load_server_key_bincode(fb_ctx* ctx, const uint8_t* buf, size_t len) {
+  if (!ctx || !buf) return fb_fail(ctx, FB_ERR_ARG, "null argument");
+  std::vector<uint64_t> ksk(FB_KSK_WORDS);
+  std::vector<double> fbsk((size_t)fb::kLweN * 4 * fb::kHalfN * 2);
+  int rc = fb_server_key_from_bincode(buf, len, ksk.data(), fbsk.data());
+  if (rc != FB_OK) return fb_fail(ctx, rc, "not a bincode tfhe::integer::ServerKey of PARAM_MESSAGE_2_CARRY_2 (layout: wire.cpp)");
+  return fb_load_server_key_fourier(ctx, ksk.data(), fbsk.data());
+}
+
+extern "C" int fb_load_server_key_raw(fb_ctx* ctx, const uint64_t* h_ksk, const uint64_t* h_bsk_std) {
+  if (!ctx || !h_ksk || !h_bsk_std) return fb_fail(ctx, FB_ERR_ARG, "null argument");
+  FB_CUDA(ctx, cudaSetDevice(ctx->device));
   {
-    cudaError_t e = cudaMemcpyAsync(d_ksk, h_ksk, FB_KSK_WORDS * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = fb::launch_ksk_bytes(d_ksk, ctx->d_kb, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_ksk);
-    if (e != cudaSuccess) return fb_cuda_fail(ctx, e, "keyswitch key upload / byte-plane split");
+    int rc = upload_ksk(ctx, h_ksk);
+    if (rc != FB_OK) return rc;
   }
   uint64_t* d_std = nullptr;
   FB_CUDA(ctx, cudaMalloc(&d_std, FB_BSK_WORDS * sizeof(uint64_t)));

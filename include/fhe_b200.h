@@ -80,6 +80,16 @@ int fb_get_option(fb_ctx* ctx, const char* name, int64_t* value);
  * (engine.rs:252, ciphertext.rs:44, mod.rs:16).  Uploads the KSK, converts the BSK to the Fourier
  * domain on the device (tfhe-rs convert_standard_lwe_bootstrap_key_to_fourier). */
 int fb_load_server_key_raw(fb_ctx* ctx, const uint64_t* h_ksk, const uint64_t* h_bsk_std);
+/* The same hand-over for a key AS THE REFERENCE HOLDS IT: a tfhe-rs 0.2.0 ServerKey keeps only the Fourier-domain
+ * bootstrapping key.  h_fbsk[742][1][2][2][1024][2] f64 (re, im): [lwe bit][level][row][polynomial][frequency] in the
+ * plan-independent natural frequency order in which tfhe-rs SERIALIZES a FourierLweBootstrapKey (its in-memory order is
+ * the FFT plan's machine-dependent permutation; see fhe_regex_b200/csrc/wire.cpp).  That is this library's resident
+ * layout, so the load is a copy: no conversion, no standard-domain key needed. */
+int fb_load_server_key_fourier(fb_ctx* ctx, const uint64_t* h_ksk, const double* h_fbsk);
+/* bincode::serialize(&tfhe::integer::ServerKey) of PARAM_MESSAGE_2_CARRY_2, exactly fb_server_key_bincode_size() bytes:
+ * the blob a maintainer gets from the value engine.rs:252 / ciphertext.rs:44 produce.  FB_ERR_FORMAT if any length or
+ * parameter differs. */
+int fb_load_server_key_bincode(fb_ctx* ctx, const uint8_t* buf, size_t len);
 /* read back the Fourier BSK ([742][2][2][1024] complex f64, natural frequency order) -- tests only */
 int fb_get_fourier_bsk(fb_ctx* ctx, double* h_out);
 
@@ -174,6 +184,22 @@ int fb_set_latency_threshold(fb_ctx* ctx, int max_count);
 int fb_set_cluster_threshold(fb_ctx* ctx, int max_count);
 /* PBS batch sizes that fill the GPU evenly are multiples of this (SM count x samples per CTA) */
 int fb_pbs_batch_quantum(fb_ctx* ctx);
+
+/* ---- tfhe-rs 0.2.0 wire formats (host only; layouts in fhe_regex_b200/csrc/wire.cpp) ---------------------------- */
+/* integer::ServerKey <-> (keyswitch key container, Fourier bootstrapping key in serialized order) */
+size_t fb_server_key_bincode_size(void);
+int fb_server_key_from_bincode(const uint8_t* buf, size_t len, uint64_t* h_ksk, double* h_fbsk);
+/* out == NULL: *written = required size */
+int fb_server_key_to_bincode(const uint64_t* h_ksk, const double* h_fbsk, uint8_t* out, size_t cap, size_t* written);
+/* integer::RadixCiphertext (ciphertext.rs:6,29): 4 shortint blocks; degrees[4] may be NULL (written as 3 = fresh) */
+size_t fb_radix_bincode_size(void);
+int fb_radix_from_bincode(const uint8_t* buf, size_t len, uint64_t* h_ct, uint64_t* degrees);
+int fb_radix_to_bincode(const uint64_t* h_ct, const uint64_t* degrees, uint8_t* out, size_t cap, size_t* written);
+/* StringCiphertext = Vec<RadixCiphertext> (ciphertext.rs:6, :32-40) <-> h_content[n_chars][4][2049], the layout
+ * fb_has_match takes.  h_content == NULL: *n_chars = number of characters in the blob.  Blocks must be fresh
+ * (degree <= 3), as encrypt_str produces them. */
+int fb_string_ciphertext_from_bincode(const uint8_t* buf, size_t len, uint64_t* h_content, size_t cap_chars, size_t* n_chars);
+int fb_string_ciphertext_to_bincode(const uint64_t* h_content, size_t n_chars, uint8_t* out, size_t cap, size_t* written);
 
 /* ---- client-side glue (tests / bench / demo only; not on the server hot path) ------------------ */
 /* Deserialize a bincode RadixClientKey like test_data/client_key (engine.rs:248-251).
