@@ -48,6 +48,11 @@ BSK_BYTES = 742 * 4 * 1024 * 16
 KS_MAC_PER_PBS = 2048 * 5 * 743
 KS_BYTES_PER_LAUNCH_KEY = 2048 * 5 * 743 * 8
 BIG, SMALL, POLY = 2049, 743, 2048
+# what the path computes in: f64 negacyclic FFT; the blind-rotation accumulator lives on the top 32 torus bits (u32,
+# narrower than the reference's u64 accumulator: DESIGN.md section 3 and tests/test_gpu_parity.py for the noise argument);
+# the keyswitch is exact mod 2^64
+DTYPE = "f64 FFT + u32 torus accumulator + u64 keyswitch (exact)"
+DTYPE_CPU = "f64 FFT + u64 torus accumulator + u64 keyswitch"
 METRIC = "bootstraps_per_sec"
 UNIT = "PBS/s"
 CK_PATH = os.path.join(ROOT, "tests", "golden", "client_key")
@@ -123,6 +128,14 @@ def make_inputs(ck, count: int, seed: int):
     return np.ascontiguousarray(np.tile(cts, (reps, 1))[:count]), np.tile(msgs, reps)[:count]
 
 
+def host_threads() -> int:
+    """host cores this process may use -- NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 to its workers"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_pbs_rate(n_samples: int, threads: int, seed: int = 0):
     """time the CPU oracle on n_samples PBS with `threads` OpenMP threads"""
     from oracle import tfhe
@@ -147,7 +160,7 @@ def run_reference(args, rank: int):
     if rank != 0:
         return
     from oracle import tfhe
-    threads = tfhe.max_threads()
+    threads = host_threads()
     per_step = max(threads * 32, 64)   # ~1-2 s of host work per step
     ock = tfhe.ClientKey.load(CK_PATH)
     osk = tfhe.keygen_server(ock, seed=0)
@@ -167,7 +180,7 @@ def run_reference(args, rank: int):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64+u64", "data": "synthetic",
+        "vs_baseline": None, "dtype": DTYPE_CPU, "data": "synthetic",
         "config": {"workload": "batched PBS (KS->BR->SE), PARAM_MESSAGE_2_CARRY_2, CPU restatement of tfhe-rs 0.2.0 (oracle/tfhe_oracle.c)",
                    "batch_per_step": per_step},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
@@ -286,7 +299,12 @@ def main():
         step_host()
     barrier()
     e2e_s = time.perf_counter() - te
-    assert (h_out.numpy().view(np.uint64)[chk[0]] == out_np[chk[0]]).all() or True  # f64 FFT: device runs are deterministic, kept lenient
+    # correctness of what the host-buffer leg produced: decrypt the same sample of ITS outputs
+    h_np = h_out.numpy().view(np.uint64)
+    for i in chk:
+        exp = fs[int(idx_np[i])](int(msgs[i])) & 15
+        got = ck.decrypt_block(h_np[i])
+        assert got == exp, "fb_pbs_batch output %d decrypts to %d, expected %d" % (i, got, exp)
 
     if world > 1:
         t = torch.tensor([ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
@@ -314,7 +332,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64+u64", "data": "synthetic",
+            "dtype": DTYPE, "data": "synthetic",
             "config": {"workload": "batched PBS (KS->BR->SE), PARAM_MESSAGE_2_CARRY_2 (n=742,N=2048,k=1), one DAG-level-sized batch of the 256-char /a+b?c/ match",
                        "batch_per_gpu": B, "global_batch": B * world, "luts": int(luts_np.shape[0]),
                        "l2": "inputs+outputs %.0f MB per step > 126 MB L2; keys (109 MB) are re-read by design" % (2 * B * BIG * 8 / 1e6),
@@ -343,7 +361,7 @@ def main():
         matches = []
         c256 = "".join(np.random.default_rng(6).choice(list("abx"), size=256))   # no 'c': every variant must be evaluated
         # (content, pattern, reference_shaped): the default plan absorbs OR operands implied by another operand
-        # (decrypt-identical, O(n) instead of O(n^2) PBS for /a+.../); FB_PLAN_NO_ABSORB=1 evaluates every variant
+        # (decrypt-identical, O(n) instead of O(n^2) PBS for /a+.../); option plan_reference_shaped evaluates every variant
         # the reference enumerates -- the large sharded PBS batch BASELINE.json's config 5 describes.
         _exp_memo = {}
 
@@ -354,39 +372,46 @@ def main():
 
         cases = [(c64, "/a+b?c/", False), (c64, "/ab{2,4}c/", False), (c64, r"/[a-d][^x-z]\./", False), (c256, "/a+b?c/", False),
                  (c64, "/a+b?c/", True), (c256, "/a+b?c/", True)]
+        # N > 1: the contexts form an NCCL communicator inside the library (fb_comm_init) and the match is the collective
+        # fb_has_match_dist: every PBS level of the plan cut into N slices, slices exchanged over NVLink in the arena --
+        # no host hop, the bitor fold is the plan's last levels.  N = 1: fb_has_match.
+        if world > 1:
+            idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+            if rank == 0:
+                idt = torch.from_numpy(np.frombuffer(fb.comm_unique_id(), dtype=np.uint8).copy()).to(dev)
+            dist.broadcast(idt, 0)
+            sk.comm_init(idt.cpu().numpy().tobytes(), rank, world)
         for content, pattern, ref_shaped in cases:
-            if ref_shaped:
-                os.environ["FB_PLAN_NO_ABSORB"] = "1"
-            else:
-                os.environ.pop("FB_PLAN_NO_ABSORB", None)
+            sk.set_option("plan_reference_shaped", 1 if ref_shaped else 0)
             ct = fb.encrypt_str(ck, content, seed=9)
+            run = (lambda: fb.has_match_dist(sk, ct, pattern, return_stats=True)) if world > 1 else \
+                  (lambda: fb.has_match(sk, ct, pattern, return_stats=True))
             barrier()
             tc = time.perf_counter()
-            fb.has_match(sk, ct, pattern, rank=rank, world=world)     # cold: parses, enumerates variants, lowers to a PBS plan
+            run()                                                      # cold: parses, enumerates variants, lowers to a PBS plan
             cold = (time.perf_counter() - tc) * 1e3
             walls = []
             for _rep in range(3):                                      # warm: plan cached in the context (same pattern, same length)
                 barrier()
                 tm = time.perf_counter()
-                part, st = fb.has_match(sk, ct, pattern, return_stats=True, rank=rank, world=world)
-                if world > 1:
-                    g = torch.from_numpy(part[0].view(np.int64)).to(dev)
-                    allg = torch.empty((world, BIG), dtype=torch.int64, device=dev)
-                    dist.all_gather_into_tensor(allg, g)
-                    if rank == 0:
-                        part = sk.or_fold(allg.cpu().numpy().view(np.uint64))
+                part, st = run()
                 barrier()
                 walls.append((time.perf_counter() - tm) * 1e3)
             wall = sorted(walls)[1]
+            if world > 1:
+                tw = torch.tensor([wall], dtype=torch.float64, device=dev)
+                dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+                wall = float(tw[0])
             if rank == 0:
                 res = ck.decrypt(part)
                 exp = expected(content, pattern)
                 assert res == exp, (pattern, res, exp)
                 matches.append({"pattern": pattern, "n_chars": len(content), "plan": "reference-shaped" if ref_shaped else "absorbed",
-                                "ms": wall, "ms_cold_rank0": cold, "gpu_ms_rank0": st["gpu_ms"], "pbs_rank0": st["pbs"],
-                                "levels": st["levels"], "level_widths_rank0": fb.plan_level_widths(pattern, len(content), rank, world),
-                                "ref_ct_ops_rank0": st["ct_ops"], "result": res})
-        os.environ.pop("FB_PLAN_NO_ABSORB", None)
+                                "ms": wall, "ms_cold_rank0": cold, "gpu_ms_rank0": st["gpu_ms"], "pbs": st["pbs"], "n_gpus": world,
+                                "levels": st["levels"], "level_widths": fb.plan_level_widths(pattern, len(content), reference_shaped=ref_shaped),
+                                "api": "fb_has_match_dist (level-sharded, NCCL in the library)" if world > 1 else "fb_has_match",
+                                "ref_ct_ops": st["ct_ops"], "result": res})
+        sk.set_option("plan_reference_shaped", 0)
         # many contents against one pattern in shared launches (fb_has_match_many): the levels are wide enough for
         # the throughput kernel, a match costs its PBS at the throughput rate instead of one latency per level
         many = []
@@ -433,9 +458,8 @@ def main():
 
     sk.close()
     if rank == 0:
-        if not args.no_cpu_baseline and world == 1:
-            from oracle import tfhe
-            threads = tfhe.max_threads()
+        if not args.no_cpu_baseline:
+            threads = host_threads()
             n = args.cpu_samples or max(256, threads * 256)   # ~10-15 s on the box's host cores
             v, dt = cpu_pbs_rate(n, threads)
             v1, dt1 = cpu_pbs_rate(64, 1)                     # ~3 s: the reference itself is single-threaded (execution.rs:76-190)

@@ -100,6 +100,11 @@ def lib():
     L.fb_radix_to_bincode.argtypes = [vp, vp, vp, sz, C.POINTER(sz)]
     L.fb_string_ciphertext_from_bincode.argtypes = [vp, sz, vp, sz, C.POINTER(sz)]
     L.fb_string_ciphertext_to_bincode.argtypes = [vp, sz, vp, sz, C.POINTER(sz)]
+    L.fb_comm_unique_id.argtypes = [vp]
+    L.fb_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.fb_comm_destroy.argtypes = [vp]
+    L.fb_comm_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.fb_has_match_dist.argtypes = [vp, vp, sz, C.c_char_p, vp, C.POINTER(MatchStats)]
     L.fb_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     L.fb_get_option.argtypes = [vp, C.c_char_p, C.POINTER(C.c_int64)]
     L.fb_kernel_stats_reset.argtypes = [vp]
@@ -435,6 +440,12 @@ class ServerKey:
         self._check(lib().fb_measure_fp64_peak(self._h, reps, C.byref(v)))
         return v.value
 
+    def comm_init(self, comm_id: bytes, rank: int, world: int):
+        """join the NCCL communicator of comm_id (fb.comm_unique_id() on rank 0, handed to the other ranks by the host)"""
+        buf = np.frombuffer(comm_id, dtype=np.uint8)
+        assert buf.size == 128
+        self._check(lib().fb_comm_init(self._h, _p(np.ascontiguousarray(buf)), rank, world))
+
     def set_option(self, name: str, value: int) -> int:
         """fb_set_option: per-context knob (include/fhe_b200.h lists them); returns the previous value"""
         prev = C.c_int64(0)
@@ -483,6 +494,23 @@ def has_match(server_key: ServerKey, content: np.ndarray, pattern: str, return_s
     st = MatchStats()
     rc = lib().fb_has_match_shard(server_key._h, _p(content) if n else None, n, pattern.encode("latin-1"), rank, world, _p(out), C.byref(st))
     server_key._check(rc)
+    return (out, st.as_dict()) if return_stats else out
+
+
+def comm_unique_id() -> bytes:
+    buf = np.zeros(128, dtype=np.uint8)
+    rc = lib().fb_comm_unique_id(_p(buf))
+    if rc != FB_OK:
+        _raise(rc, "NCCL unavailable")
+    return buf.tobytes()
+
+
+def has_match_dist(server_key: ServerKey, content: np.ndarray, pattern: str, return_stats: bool = False):
+    """collective has_match over the communicator of server_key.comm_init (fb_has_match_dist)"""
+    content = np.ascontiguousarray(content, dtype=np.uint64).reshape(-1, 4, BIG)
+    out = np.empty((4, BIG), dtype=np.uint64)
+    st = MatchStats()
+    server_key._check(lib().fb_has_match_dist(server_key._h, _p(content), content.shape[0], pattern.encode("latin-1"), _p(out), C.byref(st)))
     return (out, st.as_dict()) if return_stats else out
 
 

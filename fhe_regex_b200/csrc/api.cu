@@ -84,6 +84,7 @@ extern "C" void fb_ctx_destroy(fb_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  fb_comm_destroy(ctx);
   for (auto& p : ctx->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (auto& p : ctx->pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (auto& e : ctx->pipe_events) cudaEventDestroy(e);

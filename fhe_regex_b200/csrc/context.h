@@ -43,6 +43,10 @@ struct fb_ctx {
   bool plan_absorb = true;     // false: reference-shaped plan (option "plan_reference_shaped" = 1)
   bool plan_timing = false;    // planner phase times on stderr (option "plan_timing")
   bool have_key = false;
+  // multi-GPU: this context as a rank of an NCCL communicator (comm.cu); ncclComm_t kept opaque here
+  void* comm = nullptr;
+  int comm_rank = 0, comm_world = 1;
+  uint64_t comm_exchanges = 0, comm_bytes = 0;   // level exchanges issued / ciphertext bytes gathered per rank
   // scratch for the batch entry points
   fb_devbuf in, small, out, luts, lut_idx, digits;
   // has_match: arena of ciphertext rows, flattened plan arrays, the fixed accumulator table (uploaded once)
@@ -66,6 +70,10 @@ int fb_reserve(fb_ctx* ctx, fb_devbuf& b, size_t bytes);
     cudaError_t _e = (call);                                      \
     if (_e != cudaSuccess) return fb_cuda_fail(ctx, _e, #call);   \
   } while (0)
+
+// comm.cu: slice r of `world` contiguous slices of n items; in-place exchange of row slices over the communicator
+void fb_comm_slice(size_t n, int r, int world, size_t* lo, size_t* hi);
+int fb_comm_exchange_rows(fb_ctx* ctx, uint64_t* d_rows, size_t n, size_t row_words);
 
 // timed launches on ctx->stream (timing is a no-op unless enabled)
 int fb_run_keyswitch(fb_ctx* ctx, const uint64_t* d_in, const int32_t* d_in_rows, uint64_t* d_small, int count);

@@ -77,7 +77,11 @@ void write_trivial_radix(uint64_t* h_out, uint64_t bit) {
 
 // run m instances of a plan; instance k's input (n_in_rows x 2049, at h_in + k * n_in_rows rows) is uploaded to the
 // first n_in_rows arena rows of its block, its result radix goes to h_out_radix + k * 4 rows
-int run_plan(fb_ctx* ctx, const Plan& plan, const uint64_t* h_in, size_t n_in_rows, uint64_t* h_out_radix, double* gpu_ms, size_t m = 1) {
+// dist: the context is a rank of a communicator (comm.cu) and every rank runs this call with the same plan and input:
+// rank r uploads and bootstraps only slice r of the input rows and of every PBS level, the slices are exchanged in place
+// in the arena over NVLink, the (cheap) linear combinations are evaluated by every rank on its full copy of the arena.
+int run_plan(fb_ctx* ctx, const Plan& plan, const uint64_t* h_in, size_t n_in_rows, uint64_t* h_out_radix, double* gpu_ms, size_t m = 1,
+             bool dist = false) {
   if (plan.result_kind < 2) {
     for (size_t k = 0; k < m; k++) write_trivial_radix(h_out_radix + k * 4 * FB_LWE_BIG_WORDS, (uint64_t)plan.result_kind);
     if (gpu_ms) *gpu_ms = 0;
@@ -115,8 +119,16 @@ int run_plan(fb_ctx* ctx, const Plan& plan, const uint64_t* h_in, size_t n_in_ro
     cudaError_t _e = (call);                                                  \
     if (_e != cudaSuccess) { cleanup(); return fb_cuda_fail(ctx, _e, #call); } \
   } while (0)
-  RP_CUDA(cudaMemcpy2DAsync(d_arena, (size_t)plan.n_rows * row_bytes, h_in, n_in_rows * row_bytes, n_in_rows * row_bytes, m,
-                            cudaMemcpyHostToDevice, st));
+  dist = dist && ctx->comm && ctx->comm_world > 1 && m == 1;
+  if (dist) {   // every rank uploads its slice of the content over PCIe; NVLink does the rest
+    size_t lo, hi;
+    fb_comm_slice(n_in_rows, ctx->comm_rank, ctx->comm_world, &lo, &hi);
+    if (hi > lo)
+      RP_CUDA(cudaMemcpyAsync(d_arena + lo * FB_LWE_BIG_WORDS, h_in + lo * FB_LWE_BIG_WORDS, (hi - lo) * row_bytes, cudaMemcpyHostToDevice, st));
+  } else {
+    RP_CUDA(cudaMemcpy2DAsync(d_arena, (size_t)plan.n_rows * row_bytes, h_in, n_in_rows * row_bytes, n_in_rows * row_bytes, m,
+                              cudaMemcpyHostToDevice, st));
+  }
   RP_CUDA(cudaMemcpyAsync(d_i32, d.i32.data(), d.i32.size() * 4, cudaMemcpyHostToDevice, st));
   RP_CUDA(cudaMemcpyAsync(d_i64, d.i64.data(), d.i64.size() * 8, cudaMemcpyHostToDevice, st));
   RP_CUDA(cudaMemcpyAsync(d_u64, d.u64.data(), d.u64.size() * 8, cudaMemcpyHostToDevice, st));
@@ -129,8 +141,33 @@ int run_plan(fb_ctx* ctx, const Plan& plan, const uint64_t* h_in, size_t n_in_ro
     ctx->regex_luts_ready = true;
   }
   RP_CUDA(cudaEventRecord(ev0, st));
+  if (dist) {
+    int rc = fb_comm_exchange_rows(ctx, d_arena, n_in_rows, FB_LWE_BIG_WORDS);
+    if (rc) { cleanup(); return rc; }
+  }
   for (auto& o : d.levels) {
     int rc;
+    if (dist) {
+      if (o.n_lin > 0) {
+        rc = fb_run_lincomb(ctx, d_arena, d_i32 + o.lin_out, d_i32 + o.lin_off, d_i32 + o.lin_rows, d_i64 + o.lin_coef,
+                            d_u64 + o.lin_const, o.n_lin);
+        if (rc) { cleanup(); return rc; }
+      }
+      if (o.n_pbs > 0) {
+        size_t lo, hi;
+        fb_comm_slice((size_t)o.n_pbs, ctx->comm_rank, ctx->comm_world, &lo, &hi);
+        uint64_t* d_level_out = d_arena + (size_t)o.out_base * FB_LWE_BIG_WORDS;
+        if (hi > lo) {
+          rc = fb_run_keyswitch(ctx, d_arena, d_i32 + o.in_rows + lo, d_small, (int)(hi - lo));
+          if (rc) { cleanup(); return rc; }
+          rc = fb_run_blind_rotate(ctx, d_small, d_luts, d_u32 + o.lut_idx + lo, d_level_out + lo * FB_LWE_BIG_WORDS, nullptr, (int)(hi - lo));
+          if (rc) { cleanup(); return rc; }
+        }
+        rc = fb_comm_exchange_rows(ctx, d_level_out, (size_t)o.n_pbs, FB_LWE_BIG_WORDS);
+        if (rc) { cleanup(); return rc; }
+      }
+      continue;
+    }
     if (o.n_lin > 0) {
       rc = fb_run_lincomb(ctx, d_arena, d_i32 + o.lin_out, d_i32 + o.lin_off, d_i32 + o.lin_rows, d_i64 + o.lin_coef,
                           d_u64 + o.lin_const, o.n_lin);
@@ -268,6 +305,25 @@ extern "C" int fb_has_match_many(fb_ctx* ctx, const uint64_t* h_contents, size_t
       ms += part;
     }
   }
+  if (stats) {
+    *stats = plan->stats;
+    stats->gpu_ms = ms;
+  }
+  return FB_OK;
+}
+
+// has_match across the communicator of fb_comm_init: collective -- every rank calls it with the same content and pattern
+// and gets the result.  The plan is the single-GPU plan; its levels are sharded (run_plan, dist).
+extern "C" int fb_has_match_dist(fb_ctx* ctx, const uint64_t* h_content, size_t n_chars, const char* pattern, uint64_t* h_out,
+                                 fb_match_stats* stats) {
+  if (!ctx || !pattern || !h_out || (!h_content && n_chars)) return fb_fail(ctx, FB_ERR_ARG, "null argument");
+  if (!ctx->comm) return fb_fail(ctx, FB_ERR_ARG, "fb_has_match_dist needs fb_comm_init first");
+  std::shared_ptr<const Plan> plan;
+  int rc = cached_plan(ctx, pattern, n_chars, 0, 1, plan);
+  if (rc != FB_OK) return rc;
+  double ms = 0;
+  rc = run_plan(ctx, *plan, h_content, 4 * n_chars, h_out, &ms, 1, true);
+  if (rc != FB_OK) return rc;
   if (stats) {
     *stats = plan->stats;
     stats->gpu_ms = ms;

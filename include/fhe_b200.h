@@ -140,6 +140,24 @@ int fb_has_match_many(fb_ctx* ctx, const uint64_t* h_contents, size_t n_contents
  * carries the reference's counters of the whole match and pbs / levels of this rank's plan. */
 int fb_has_match_shard(fb_ctx* ctx, const uint64_t* h_content, size_t n_chars, const char* pattern, int rank, int world,
                        uint64_t* h_out, fb_match_stats* stats);
+/* ---- multi-GPU: one process per GPU, every context a rank of one NCCL communicator (keys replicated) ------------- */
+#define FB_COMM_ID_BYTES 128
+/* rank 0 makes an id (an ncclUniqueId) and hands it to the other ranks by whatever means the host has (MPI, a store,
+ * torch.distributed.broadcast ...); then every rank joins.  NCCL is loaded at run time; FB_ERR_NO_DEVICE if absent. */
+int fb_comm_unique_id(uint8_t* id /* [FB_COMM_ID_BYTES] */);
+int fb_comm_init(fb_ctx* ctx, const uint8_t* id, int rank, int world);
+int fb_comm_destroy(fb_ctx* ctx);
+int fb_comm_info(fb_ctx* ctx, int* rank, int* world);
+/* has_match (engine.rs:8-42) across the communicator -- COLLECTIVE: every rank calls it with the same content and
+ * pattern, every rank gets the result in h_out.  Each PBS level of the plan is cut into `world` contiguous slices, rank r
+ * bootstraps slice r, and the slices are exchanged device to device over NVLink (grouped ncclBroadcast, in place in the
+ * ciphertext arena, on the context stream): no host round trip between levels, and the final bitor fold of the reference
+ * (engine.rs:22-35) is simply the last levels of the same plan.  Rank r reads only slice r of h_content (the content is
+ * uploaded over PCIe once in total and gathered over NVLink).  stats: the plan's counters (whole match) and this rank's
+ * device time. */
+int fb_has_match_dist(fb_ctx* ctx, const uint64_t* h_content, size_t n_chars, const char* pattern, uint64_t* h_out,
+                      fb_match_stats* stats);
+
 /* OR of n single-block booleans h_in[n][2049] -> h_out[4][2049] radix (the final fold, engine.rs:30-33) */
 int fb_or_fold(fb_ctx* ctx, const uint64_t* h_in, size_t n, uint64_t* h_out);
 

@@ -281,9 +281,13 @@ def test_has_match_64_char_configs(fck, gpu_key):
     c64 = "".join(rng.choice(list("abcx"), size=64))
     planted = c64[:20] + "xaabc" + c64[25:]
     for content, pattern in [(c64, r"/[a-d][^x-z]\./"), (planted, "/ab{2,4}c/"), (c64, "/ab{2,4}c/"), (planted, "/a+b?c/"),
-                             ("x" * 64, "/a+b?c/"), (c64, r"/^[a-d][^x-z]\.$/")]:
+                             ("x" * 64, "/a+b?c/"), (c64, r"/^[a-d][^x-z]\.$/"), (c64, "/^ab{2,4}c$/")]:
         res = fb.has_match(gpu_key, fb.encrypt_str(fck, content, seed=9), pattern)
         assert fck.decrypt(res) == rp.has_match(content, pattern), (content, pattern)
+    # BASELINE config 4 read literally: an anchored pattern of at most 6 characters against 64 characters has no
+    # variant at all (engine.rs:59-65): 0 ciphertext operations, a trivial encryption of false
+    res, st = fb.has_match(gpu_key, fb.encrypt_str(fck, c64, seed=9), "/^ab{2,4}c$/", return_stats=True)
+    assert (st["variants"], st["ct_ops"], st["pbs"]) == (0, 0, 0) and fck.decrypt(res) == 0 and (res[:, :2048] == 0).all()
 
 
 def test_has_match_256_char_config5_both_plans(fck, gpu_key):
@@ -371,6 +375,23 @@ def test_bootstrap_noise_worst_case_input():
     assert res["decryption_failures"] == 0, res
     assert res["err_std"] < PBS_ERR_STD_MAX and res["err_abs_max"] < PBS_ERR_MAX, res
     assert min(res["input_sum_histogram"][3:13]) > 0      # the sums really spread over the boxes
+
+
+def test_has_match_dist_single_rank_communicator(fck, server_key):
+    """fb_comm_init + fb_has_match_dist with a communicator of one rank (what a 1-GPU box can run; the multi-rank path is
+    exercised by tools/dist_match_check.py under torchrun, profiles/r02_dist_n*.log): same decryption as fb_has_match."""
+    sk = fb.ServerKey(server_key.ksk, server_key.bsk)
+    try:
+        sk.comm_init(fb.comm_unique_id(), 0, 1)
+        for content, pattern in (("xabbcx", "/ab{2,4}c/"), ("aq.", r"/^[a-d][^x-z]\.$/"), ("", "/^$/")):
+            ct = fb.encrypt_str(fck, content, seed=5)
+            res, st = fb.has_match_dist(sk, ct, pattern, return_stats=True)
+            assert fck.decrypt(res) == rp.has_match(content, pattern) == fck.decrypt(fb.has_match(sk, ct, pattern))
+    finally:
+        sk.close()
+    with pytest.raises(fb.FbError):
+        fb.has_match_dist(sk2 := fb.ServerKey(server_key.ksk, server_key.bsk), fb.trivial_str("a"), "/a/")   # no communicator
+    sk2.close()
 
 
 def test_server_key_in_the_references_own_form(client_key, server_key, gpu_key, fck):
