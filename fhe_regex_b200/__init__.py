@@ -100,6 +100,14 @@ def lib():
     L.fb_radix_to_bincode.argtypes = [vp, vp, vp, sz, C.POINTER(sz)]
     L.fb_string_ciphertext_from_bincode.argtypes = [vp, sz, vp, sz, C.POINTER(sz)]
     L.fb_string_ciphertext_to_bincode.argtypes = [vp, sz, vp, sz, C.POINTER(sz)]
+    L.fb_ct_alloc.argtypes = [vp, sz, sz, C.POINTER(C.c_uint64)]
+    L.fb_ct_free.argtypes = [vp, C.c_uint64]
+    L.fb_ct_upload.argtypes = [vp, C.c_uint64, sz, vp, sz]
+    L.fb_ct_download.argtypes = [vp, C.c_uint64, sz, sz, vp]
+    L.fb_lincomb.argtypes = [vp, C.c_uint64, vp, vp, vp, vp, vp, sz]
+    L.fb_pbs_rows.argtypes = [vp, C.c_uint64, vp, C.c_uint64, vp, sz, sz]
+    L.fb_plan_export.argtypes = [C.c_char_p, sz, C.c_uint32, vp, sz, C.POINTER(sz)]
+    L.fb_regex_lut_table.argtypes = [vp]
     L.fb_comm_unique_id.argtypes = [vp]
     L.fb_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
     L.fb_comm_destroy.argtypes = [vp]
@@ -440,6 +448,42 @@ class ServerKey:
         self._check(lib().fb_measure_fp64_peak(self._h, reps, C.byref(v)))
         return v.value
 
+    # ---- op-level boundary: device arenas (include/fhe_b200.h, handles.cu) ----
+    def ct_alloc(self, rows: int, row_words: int = BIG) -> int:
+        h = C.c_uint64(0)
+        self._check(lib().fb_ct_alloc(self._h, rows, row_words, C.byref(h)))
+        return int(h.value)
+
+    def ct_free(self, h: int):
+        self._check(lib().fb_ct_free(self._h, h))
+
+    def ct_upload(self, h: int, first_row: int, rows: np.ndarray):
+        rows = np.ascontiguousarray(rows, dtype=np.uint64)
+        rows = rows.reshape(-1, rows.shape[-1])
+        self._check(lib().fb_ct_upload(self._h, h, first_row, _p(rows), rows.shape[0]))
+
+    def ct_download(self, h: int, first_row: int, count: int, row_words: int = BIG) -> np.ndarray:
+        out = np.empty((count, row_words), dtype=np.uint64)
+        self._check(lib().fb_ct_download(self._h, h, first_row, count, _p(out)))
+        return out
+
+    def lincomb(self, h: int, out_rows, term_off, term_rows, term_coef, body_const):
+        a = [np.ascontiguousarray(out_rows, dtype=np.int32), np.ascontiguousarray(term_off, dtype=np.int32),
+             np.ascontiguousarray(term_rows, dtype=np.int32), np.ascontiguousarray(term_coef, dtype=np.int64),
+             np.ascontiguousarray(body_const, dtype=np.uint64)]
+        if a[0].size == 0:
+            return
+        assert a[1].size == a[0].size + 1 and a[4].size == a[0].size and a[2].size == a[3].size == a[1][-1]
+        ptr = [_p(x) if x.size else None for x in a]
+        self._check(lib().fb_lincomb(self._h, h, ptr[0], ptr[1], ptr[2], ptr[3], ptr[4], a[0].size))
+
+    def pbs_rows(self, h: int, in_rows, luts_h: int, lut_idx, out_row_base: int):
+        rows = np.ascontiguousarray(in_rows, dtype=np.int32)
+        idx = np.ascontiguousarray(lut_idx, dtype=np.uint32)
+        assert rows.size == idx.size
+        if rows.size:
+            self._check(lib().fb_pbs_rows(self._h, h, _p(rows), luts_h, _p(idx), rows.size, out_row_base))
+
     def comm_init(self, comm_id: bytes, rank: int, world: int):
         """join the NCCL communicator of comm_id (fb.comm_unique_id() on rank 0, handed to the other ranks by the host)"""
         buf = np.frombuffer(comm_id, dtype=np.uint8)
@@ -495,6 +539,48 @@ def has_match(server_key: ServerKey, content: np.ndarray, pattern: str, return_s
     rc = lib().fb_has_match_shard(server_key._h, _p(content) if n else None, n, pattern.encode("latin-1"), rank, world, _p(out), C.byref(st))
     server_key._check(rc)
     return (out, st.as_dict()) if return_stats else out
+
+
+def regex_lut_table() -> np.ndarray:
+    out = np.empty((51, POLY), dtype=np.uint64)
+    rc = lib().fb_regex_lut_table(_p(out))
+    if rc != FB_OK:
+        _raise(rc, "fb_regex_lut_table")
+    return out
+
+
+def plan_export(pattern: str, n_chars: int, reference_shaped: bool = False) -> dict:
+    """the library's level-synchronous plan of a match (fb_plan_export), parsed into python lists"""
+    flags = PLAN_REFERENCE_SHAPED if reference_shaped else 0
+    n = C.c_size_t(0)
+    rc = lib().fb_plan_export(pattern.encode("latin-1"), n_chars, flags, None, 0, C.byref(n))
+    if rc != FB_OK:
+        _raise(rc, "plan failed for %r" % pattern)
+    w = np.empty(n.value, dtype=np.int64)
+    rc = lib().fb_plan_export(pattern.encode("latin-1"), n_chars, flags, _p(w), w.size, C.byref(n))
+    if rc != FB_OK:
+        _raise(rc, "plan export failed")
+    pos = [0]
+
+    def take(k):
+        v = w[pos[0]:pos[0] + k]
+        pos[0] += k
+        return v
+
+    n_rows, kind, res_row, n_levels = (int(x) for x in take(4))
+    levels = []
+    for _ in range(n_levels):
+        n_lin, n_terms, n_pbs, base = (int(x) for x in take(4))
+        lv = {"out_row_base": base, "lin_out_rows": take(n_lin).astype(np.int32)}
+        lv["lin_term_off"] = take(n_lin + 1 if n_lin else 1).astype(np.int32)
+        lv["lin_term_rows"] = take(n_terms).astype(np.int32)
+        lv["lin_coef"] = take(n_terms).copy()
+        lv["lin_const"] = take(n_lin).view(np.uint64).copy()
+        lv["in_rows"] = take(n_pbs).astype(np.int32)
+        lv["lut_idx"] = take(n_pbs).astype(np.uint32)
+        levels.append(lv)
+    assert pos[0] == w.size
+    return {"n_rows": n_rows, "result_kind": kind, "result_row": res_row, "levels": levels}
 
 
 def comm_unique_id() -> bytes:

@@ -94,7 +94,9 @@ extern "C" void fb_ctx_destroy(fb_ctx* ctx) {
   cudaFree(ctx->d_fbsk);
   cudaFree(ctx->d_tabs);
   for (fb_devbuf* b : {&ctx->in, &ctx->small, &ctx->out, &ctx->luts, &ctx->lut_idx, &ctx->digits, &ctx->arena, &ctx->plan_i32,
-                       &ctx->plan_i64, &ctx->plan_u64, &ctx->plan_u32, &ctx->regex_luts}) cudaFree(b->p);
+                       &ctx->plan_i64, &ctx->plan_u64, &ctx->plan_u32, &ctx->regex_luts, &ctx->op_i32, &ctx->op_i64, &ctx->op_u64,
+                       &ctx->op_u32, &ctx->op_rows}) cudaFree(b->p);
+  for (auto& a : ctx->arenas) cudaFree(a.p);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

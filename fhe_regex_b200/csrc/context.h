@@ -16,6 +16,12 @@ struct fb_devbuf {
   size_t cap = 0;
 };
 
+// a device-resident array of ciphertext rows (2049 words) or accumulator polynomials (2048 words) behind an fb_handle
+struct fb_arena {
+  uint64_t* p = nullptr;
+  size_t rows = 0, row_words = 0;
+};
+
 struct fb_event_pair {
   cudaEvent_t a, b;
   int kind;  // 0 ks, 1 br, 2 lin
@@ -52,6 +58,9 @@ struct fb_ctx {
   // has_match: arena of ciphertext rows, flattened plan arrays, the fixed accumulator table (uploaded once)
   fb_devbuf arena, plan_i32, plan_i64, plan_u64, plan_u32, regex_luts;
   bool regex_luts_ready = false;
+  // op-level boundary (handles.cu): caller-visible arenas and the staging buffers of their index arrays
+  std::vector<fb_arena> arenas;
+  fb_devbuf op_i32, op_i64, op_u64, op_u32, op_rows;
   // lowered plans of recent (pattern, content length, rank, world) requests: the plan depends on nothing else, so a
   // server matching many contents against one pattern builds it once (most recent first, at most 8)
   std::vector<std::pair<std::string, std::shared_ptr<const fbre::Plan>>> plan_cache;

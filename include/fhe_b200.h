@@ -179,6 +179,32 @@ int fb_plan_level_widths(const char* pattern, size_t n_chars, int rank, int worl
  * result = what decrypt(has_match(..)) would give for this rank's share; used to test the lowering. */
 int fb_plan_eval_plain(const char* pattern, const uint8_t* content, size_t n_chars, int rank, int world, uint32_t flags, int* result);
 
+/* ---- op-level boundary: device-resident arenas for a host that keeps its own executor ---------------------------- */
+/* For a maintainer who keeps `Execution` (execution.rs:37-223: the six smart_* call sites :76,93,110,143,173,190 and the
+ * structural cache with_cache :212-222) and only swaps the arithmetic: ciphertexts live in an arena on the GPU, a level
+ * of cache-missing ops is flushed as one fb_lincomb (packing, sums of booleans, NOT) plus one fb_pbs_rows (KS -> BR -> SE
+ * through per-row LUTs), and nothing returns to the host until the result is downloaded.  All calls are asynchronous on
+ * fb_ctx_stream() except fb_ct_download. */
+typedef uint64_t fb_handle;   /* 0 is never a valid handle */
+#define FB_REGEX_LUTS 51      /* rows of the accumulator table of fb_has_match (fb_regex_lut_table) */
+/* rows x row_words u64 on the device; row_words = 2049 (LWE ciphertexts under the big key) or 2048 (LUT polynomials) */
+int fb_ct_alloc(fb_ctx* ctx, size_t rows, size_t row_words, fb_handle* out);
+int fb_ct_free(fb_ctx* ctx, fb_handle h);
+int fb_ct_upload(fb_ctx* ctx, fb_handle h, size_t first_row, const uint64_t* h_rows, size_t count);
+int fb_ct_download(fb_ctx* ctx, fb_handle h, size_t first_row, size_t count, uint64_t* h_rows);   /* synchronizes */
+/* arena[out_rows[o]] = sum over t in [term_off[o], term_off[o+1]) of term_coef[t] * arena[term_rows[t]]
+ *                      + trivial(body_const[o])         -- bivariate packing, k-ary sums, 1 - x; o < n_out */
+int fb_lincomb(fb_ctx* ctx, fb_handle h, const int32_t* h_out_rows, const int32_t* h_term_off, const int32_t* h_term_rows,
+               const int64_t* h_term_coef, const uint64_t* h_body_const, size_t n_out);
+/* arena[out_row_base + b] = PBS(arena[in_rows[b]], luts[lut_idx[b]]), b < count  (what every smart_* block op is) */
+int fb_pbs_rows(fb_ctx* ctx, fb_handle h, const int32_t* h_in_rows, fb_handle luts, const uint32_t* h_lut_idx, size_t count,
+                size_t out_row_base);
+/* The library's own level-synchronous plan of a match as a stream of int64 (layout: handles.cu), so that a host can
+ * drive or check it level by level with the calls above.  out == NULL: *n_words = required length.  Host only. */
+int fb_plan_export(const char* pattern, size_t n_chars, uint32_t flags, int64_t* out, size_t cap, size_t* n_words);
+/* the accumulator table fb_has_match bootstraps through: h_out[FB_REGEX_LUTS][2048].  Host only. */
+int fb_regex_lut_table(uint64_t* h_out);
+
 /* ---- timing ----------------------------------------------------------------------------------- */
 typedef struct fb_kernel_stats {
   uint64_t ks_launches, br_launches, lin_launches;

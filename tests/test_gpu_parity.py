@@ -377,6 +377,54 @@ def test_bootstrap_noise_worst_case_input():
     assert min(res["input_sum_histogram"][3:13]) > 0      # the sums really spread over the boxes
 
 
+def test_handle_api_replays_has_match_level_by_level(fck, gpu_key):
+    """The op-level boundary (fb_ct_alloc / fb_ct_upload / fb_lincomb / fb_pbs_rows / fb_ct_download) driven from the host
+    with the library's own plan (fb_plan_export): a host that keeps the reference's Execution (execution.rs:64-222) flushes
+    its levels exactly like this.  Same kernels on the same rows: the result row is bit-identical to fb_has_match's."""
+    luts = fb.regex_lut_table()
+    for content, pattern in (("xabbcx", "/ab{2,4}c/"), ("bq.", r"/^[a-d][^x-z]\.$/"), ("xxaBcxxxxxxxxxxx", "/abc/i")):
+        ct = fb.encrypt_str(fck, content, seed=5)
+        ref = fb.has_match(gpu_key, ct, pattern)
+        plan = fb.plan_export(pattern, len(content))
+        assert plan["result_kind"] == 2
+        arena = gpu_key.ct_alloc(plan["n_rows"])
+        lut_h = gpu_key.ct_alloc(luts.shape[0], 2048)
+        try:
+            gpu_key.ct_upload(lut_h, 0, luts)
+            gpu_key.ct_upload(arena, 0, ct.reshape(-1, 2049))
+            for lv in plan["levels"]:
+                gpu_key.lincomb(arena, lv["lin_out_rows"], lv["lin_term_off"], lv["lin_term_rows"], lv["lin_coef"], lv["lin_const"])
+                gpu_key.pbs_rows(arena, lv["in_rows"], lut_h, lv["lut_idx"], lv["out_row_base"])
+            got = gpu_key.ct_download(arena, plan["result_row"], 1)[0]
+        finally:
+            gpu_key.ct_free(arena)
+            gpu_key.ct_free(lut_h)
+        assert (got == ref[0]).all()
+        assert fck.decrypt_block(got) == rp.has_match(content, pattern)
+    # argument checking: rows out of range, wrong kind of arena
+    arena = gpu_key.ct_alloc(4)
+    with pytest.raises(fb.FbError):
+        gpu_key.pbs_rows(arena, [0], arena, [0], 0)              # LUT handle must hold 2048-word rows
+    with pytest.raises(fb.FbError):
+        gpu_key.lincomb(arena, [4], [0, 1], [0], [1], [0])       # output row out of range
+    with pytest.raises(fb.FbError):
+        gpu_key.ct_download(arena, 3, 2)
+    gpu_key.ct_free(arena)
+    with pytest.raises(fb.FbError):
+        gpu_key.ct_free(arena)
+
+
+def test_every_kernel_on_a_small_ragged_case():
+    """tools/sanitize_case.py: sparse-mask inputs (12 CMUX steps per rotation) through every kernel at ragged batch sizes,
+    checked against the oracle -- the case compute-sanitizer was to run (the tool is closed on this pool:
+    profiles/r02_sanitizer_closed.txt)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("sanitize_case", os.path.join(os.path.dirname(__file__), "..", "tools", "sanitize_case.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.main()
+
+
 def test_has_match_dist_single_rank_communicator(fck, server_key):
     """fb_comm_init + fb_has_match_dist with a communicator of one rank (what a 1-GPU box can run; the multi-rank path is
     exercised by tools/dist_match_check.py under torchrun, profiles/r02_dist_n*.log): same decryption as fb_has_match."""
