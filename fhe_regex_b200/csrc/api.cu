@@ -92,6 +92,7 @@ extern "C" void fb_ctx_destroy(fb_ctx* ctx) {
   if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
   cudaFree(ctx->d_kb);
   cudaFree(ctx->d_fbsk);
+  cudaFree(ctx->d_fbsk_lm);
   cudaFree(ctx->d_tabs);
   for (fb_devbuf* b : {&ctx->in, &ctx->small, &ctx->out, &ctx->luts, &ctx->lut_idx, &ctx->digits, &ctx->arena, &ctx->plan_i32,
                        &ctx->plan_i64, &ctx->plan_u64, &ctx->plan_u32, &ctx->regex_luts, &ctx->op_i32, &ctx->op_i64, &ctx->op_u64,
@@ -112,6 +113,7 @@ extern "C" int fb_sync(fb_ctx* ctx) {
 // keyswitch key: upload the u64 container, keep only its byte planes resident
 static int upload_ksk(fb_ctx* ctx, const uint64_t* h_ksk) {
   if (!ctx->d_fbsk) FB_CUDA(ctx, cudaMalloc(&ctx->d_fbsk, (size_t)fb::kLweN * 4 * fb::kHalfN * sizeof(c2)));
+  if (!ctx->d_fbsk_lm) FB_CUDA(ctx, cudaMalloc(&ctx->d_fbsk_lm, (size_t)fb::kLweN * 4 * fb::kHalfN * sizeof(c2)));
   if (!ctx->d_kb) FB_CUDA(ctx, cudaMalloc(&ctx->d_kb, fb::ks_key_bytes()));
   uint64_t* d_ksk = nullptr;  // staging copy of the u64 key; only its byte planes stay resident
   FB_CUDA(ctx, cudaMalloc(&d_ksk, FB_KSK_WORDS * sizeof(uint64_t)));
@@ -131,6 +133,7 @@ extern "C" int fb_load_server_key_fourier(fb_ctx* ctx, const uint64_t* h_ksk, co
   int rc = upload_ksk(ctx, h_ksk);
   if (rc != FB_OK) return rc;
   FB_CUDA(ctx, cudaMemcpyAsync(ctx->d_fbsk, h_fbsk, (size_t)fb::kLweN * 4 * fb::kHalfN * sizeof(c2), cudaMemcpyHostToDevice, ctx->stream));
+  FB_CUDA(ctx, fb::launch_fbsk_lane_major(ctx->d_fbsk, ctx->d_fbsk_lm, ctx->stream));
   FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->have_key = true;
   return FB_OK;
@@ -157,6 +160,7 @@ extern "C" int fb_load_server_key_raw(fb_ctx* ctx, const uint64_t* h_ksk, const 
   FB_CUDA(ctx, cudaMalloc(&d_std, FB_BSK_WORDS * sizeof(uint64_t)));
   cudaError_t e = cudaMemcpyAsync(d_std, h_bsk_std, FB_BSK_WORDS * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = fb::launch_bsk_convert(d_std, ctx->d_fbsk, ctx->d_tabs, ctx->stream);
+  if (e == cudaSuccess) e = fb::launch_fbsk_lane_major(ctx->d_fbsk, ctx->d_fbsk_lm, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   cudaFree(d_std);
   if (e != cudaSuccess) return fb_cuda_fail(ctx, e, "key upload / Fourier conversion");
@@ -263,7 +267,7 @@ int fb_run_blind_rotate(fb_ctx* ctx, const uint64_t* d_small, const uint64_t* d_
     const int head = (tail > 0 && tail <= narrow_max) ? count - tail : count;
     // the fused body is built for 4 PBS per SM: batches that do not fill the GPU at that width keep the phase-by-phase body
     const bool fused = ctx->br_variant >= 1 && head > 3 * (q / fb::br_samples_per_cta());
-    e = fused ? fb::launch_blind_rotate_fused(ctx->d_fbsk, d_small, d_luts, d_lut_idx, d_out, d_out_rows, ctx->d_tabs, head, ctx->br_variant - 1, ctx->stream)
+    e = fused ? fb::launch_blind_rotate_fused(ctx->d_fbsk, ctx->d_fbsk_lm, d_small, d_luts, d_lut_idx, d_out, d_out_rows, ctx->d_tabs, head, ctx->br_variant - 1, ctx->stream)
               : fb::launch_blind_rotate(ctx->d_fbsk, d_small, d_luts, d_lut_idx, d_out, d_out_rows, ctx->d_tabs, head, ctx->stream);
     if (e == cudaSuccess && head < count)
       e = narrow(d_small + (size_t)head * FB_LWE_SMALL_WORDS, d_lut_idx + head, d_out_rows ? d_out : d_out + (size_t)head * FB_LWE_BIG_WORDS,
@@ -322,7 +326,7 @@ struct OptionDesc { const char* name; int64_t lo, hi; };
 const OptionDesc kOptions[] = {
     {"latency_threshold", 0, 1 << 30},      // = fb_set_latency_threshold
     {"cluster_threshold", 0, 1 << 30},      // = fb_set_cluster_threshold
-    {"br_variant", 0, 2},                   // throughput blind rotation: 0 phase-by-phase body, 1 fused body, 2 fused + digits via I2F
+    {"br_variant", 0, 4},                   // throughput blind rotation: 0 phase-by-phase body, 1 fused, 2 fused + I2F digits, 3 fused + TMEM key, 4 both
     {"wide_skew", 0, 100000},               // latency kernel: hold-back of one CTA half after the MAC, cycles
     {"wide_prefetch", 0, 4},                // latency kernel: GGSW groups fetched before the pre-MAC barrier
     {"plan_reference_shaped", 0, 1},        // 1: evaluate every variant the reference enumerates (no absorption)

@@ -42,6 +42,57 @@ __device__ __forceinline__ void mid_block(double (&xr)[32], double (&xi)[32], co
   fft32_inv_s3<B>(xr, xi);
 }
 
+// The same block with the key served from tensor memory: the thread's 64 key values of the step sit in 256 columns of its own
+// TMEM lane in MAC order (slot q: own at columns 8q..8q+3, in at 8q+4..8q+7; layout fbsk_lm_kernel), four slots per
+// tcgen05.ld -- no shared-memory wavefronts for the key (tools/microbench/tmem_ld_probe.cu: > 700 B/cycle/SM).
+template <int H>
+__device__ __forceinline__ void mac_half_tmem(double (&xr)[32], double (&xi)[32], const uint32_t (&kv)[32]) {
+#pragma unroll
+  for (int t = 0; t < 4; t++) {
+    const int q = 4 * H + t;
+    const double pr = __shfl_xor_sync(0xffffffffu, xr[q], 16);
+    const double pi = __shfl_xor_sync(0xffffffffu, xi[q], 16);
+    c2 g_own, g_in;
+    g_own.x = __hiloint2double((int)kv[8 * t + 1], (int)kv[8 * t]);
+    g_own.y = __hiloint2double((int)kv[8 * t + 3], (int)kv[8 * t + 2]);
+    g_in.x = __hiloint2double((int)kv[8 * t + 5], (int)kv[8 * t + 4]);
+    g_in.y = __hiloint2double((int)kv[8 * t + 7], (int)kv[8 * t + 6]);
+    mac_point2(xr[q], xi[q], pr, pi, g_own, g_in);
+  }
+}
+// block B of the middle section, software-pipelined on the tensor-memory reads: the key values of a half (4 slots, 32
+// columns) are requested one half ahead, so that a tcgen05.wait::ld finds them there.  ka / kb alternate; on entry the load
+// of half 2B into ka is in flight, on exit the load of half 2B + 2 (if any).
+template <int B>
+__device__ __forceinline__ void mid_block_tmem(double (&xr)[32], double (&xi)[32], uint32_t tkey, uint32_t (&ka)[32], uint32_t (&kb)[32]) {
+  fft32_fwd_s3<B>(xr, xi);
+  fft32_fwd_s45<2 * B>(xr, xi);
+  tmem_ld32_wait(ka);
+  tmem_ld32_issue(tkey + 32 * (2 * B + 1), kb);
+  mac_half_tmem<2 * B>(xr, xi, ka);
+  fft32_fwd_s45<2 * B + 1>(xr, xi);
+  tmem_ld32_wait(kb);
+  if (B < 3) tmem_ld32_issue(tkey + 32 * (2 * B + 2), ka);
+  mac_half_tmem<2 * B + 1>(xr, xi, kb);
+  fft32_inv_s12<2 * B>(xr, xi);
+  fft32_inv_s12<2 * B + 1>(xr, xi);
+  fft32_inv_s3<B>(xr, xi);
+}
+
+// the Fourier key re-ordered for the tensor-memory path: per step 64 chunks of 64 rows of one complex value;
+// chunk j = 2q + o (MAC slot q, o = 0: own column, 1: the other row's), row r = 32 w + L (warp parity w, lane L)
+__global__ void __launch_bounds__(256)
+fbsk_lm_kernel(const c2* __restrict__ fbsk, c2* __restrict__ fbsk_lm) {
+  const size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x;      // (i, j, r)
+  if (idx >= (size_t)kLweN * 4096) return;
+  const int r = (int)(idx & 63), j = (int)((idx >> 6) & 63), i = (int)(idx >> 12);
+  const int w = r >> 5, L = r & 31, pp = L >> 4, k1 = 16 * w + (L & 15);
+  const int q = j >> 1, o = j & 1;
+  const int k = k1 + 32 * brev5(q);
+  const int pin = o ? 1 - pp : pp;
+  fbsk_lm[idx] = fbsk[fbsk_index(i, pin, pp, k)];
+}
+
 // phase C for the two slots of last-stage butterfly A (slots A and A+16): increments into the TMEM words and the
 // shared-memory copy.  lo / hi: the 16 TMEM words of register groups A/8 and A/8 + 2.
 template <int A>
@@ -79,7 +130,8 @@ __device__ __forceinline__ void fin_half(double (&xr)[32], double (&xi)[32], uin
 }
 
 // Same launch geometry, shared-memory layout and hand-over protocol as kernels.cu::blind_rotate_kernel<S>.
-// V: bit 0 = digits through the integer-to-double conversion unit
+// V: bit 0 = digits through the integer-to-double conversion unit; bit 1 = Fourier key of the step staged in tensor memory
+// (fbsk then points to the re-ordered key of fbsk_lm_kernel)
 template <int S, int V>
 __global__ void __launch_bounds__(64 * S, 1)
 blind_rotate_fused_kernel(const c2* __restrict__ fbsk, const uint64_t* __restrict__ small, const uint64_t* __restrict__ luts,
@@ -95,8 +147,11 @@ blind_rotate_fused_kernel(const c2* __restrict__ fbsk, const uint64_t* __restric
   uint16_t* at_all = reinterpret_cast<uint16_t*>(tab_i + kTabEntries * 32);             // [S][768]
   uint8_t* need = reinterpret_cast<uint8_t*>(at_all + S * 768);                         // [768]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(need + 768);                         // GGSW bytes have landed
-  uint32_t* done_cnt = reinterpret_cast<uint32_t*>(full_bar + 1);                       // warps done with the stage
+  uint64_t* tkey_bar = full_bar + 1;                                                    // (V & 2) GGSW copied into tensor memory
+  uint64_t* macdone_bar = tkey_bar + 1;                                                 // (V & 2) every warp is past its MAC of the step
+  uint32_t* done_cnt = reinterpret_cast<uint32_t*>(macdone_bar + 1);                    // warps done with the stage
   uint32_t* tmem_slot = done_cnt + 1;
+  constexpr bool kTKey = (V & 2) != 0;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int s = warp >> 1, w = warp & 1;
@@ -107,6 +162,8 @@ blind_rotate_fused_kernel(const c2* __restrict__ fbsk, const uint64_t* __restric
   for (int t = tid; t < 2 * kTabEntries * 32; t += 64 * S) tab_f[t] = tabs_g[t];
   if (tid == 0) {
     mbar_init(full_bar, 1);
+    mbar_init(tkey_bar, n_warps_active > 0 ? n_warps_active : 1);   // one tcgen05.commit per active warp and step
+    mbar_init(macdone_bar, n_warps_active > 0 ? n_warps_active : 1);
     *done_cnt = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -155,11 +212,47 @@ blind_rotate_fused_kernel(const c2* __restrict__ fbsk, const uint64_t* __restric
       }
     }
   };
-  if (tid == 0) {
-    int j = 0;
+  // ---- tensor-memory key (V & 2) ----------------------------------------------------------------------------------
+  // e = number of steps this CTA has executed so far.  The key of executed step e travels: HBM -> (bulk copy #e) -> the
+  // shared-memory stage -> (tcgen05.cp, 64 chunks spread over the active warps' lane 0) -> TMEM columns [128, 384) of every lane.
+  //   MAC of step e:      wait tkey_bar phase e; thread 0 then issues bulk copy #e+1 (the stage is free: the copies into TMEM
+  //                       that read it have completed); after its MAC a warp bumps done_cnt.
+  //   later in step e:    every warp waits until all warps are past their MAC (done_cnt) and bulk copy #e+1 has landed, its
+  //                       lane 0 issues its share of the tcgen05.cp of key e+1 and commits to tkey_bar.
+  const uint32_t tkey = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 128u;
+  auto next_needed = [&](int i) {
+    int j = i + 1;
     while (j < kLweN && !need[j]) j++;
-    if (j < kLweN) issue_ggsw(j);
-  }
+    return j;
+  };
+  const uint32_t uwarp = (uint32_t)__shfl_sync(0xffffffffu, warp, 0);   // provably warp-uniform: the copy operands stay in uniform registers
+  auto stage_key_to_tmem = [&](uint32_t e) {   // copies of executed step e's key, issued at the top of that step; warp-uniform
+    if (e > 0) mbar_wait(macdone_bar, (e - 1u) & 1u);   // every warp is past its MAC of step e - 1 (hardware sleep, no spinning:
+                                                        // a spinning warp would take issue slots from the warp it waits for)
+    mbar_wait(full_bar, e & 1u);
+    tmem_fence_after();
+    if (lane == 0) {
+      const uint64_t d0 = tmem_cp_desc(smem_u32(smem));
+      if (n_warps_active == 8u) {
+#pragma unroll
+        for (uint32_t u = 0; u < 8u; u++) {
+          const uint32_t j = uwarp + 8u * u;
+          tmem_cp_64x128b_02_13(tmem_base + 128u + 4u * j, d0 + 64u * j);
+        }
+      } else {
+        for (uint32_t j = uwarp; j < 64u; j += n_warps_active) tmem_cp_64x128b_02_13(tmem_base + 128u + 4u * j, d0 + 64u * j);
+      }
+      tmem_commit(tkey_bar);
+    }
+    __syncwarp();
+  };
+  auto mac_done = [&]() {
+    tmem_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(macdone_bar);
+  };
+  const int first_step = next_needed(-1);
+  if (tid == 0 && first_step < kLweN) issue_ggsw(first_step);
 
   if (active) {
     const uint32_t shp_off = (uint32_t)kGgswBytes + (uint32_t)(s * 2 + w) * 8192u;   // byte offset of this polynomial's accumulator copy
@@ -197,10 +290,18 @@ blind_rotate_fused_kernel(const c2* __restrict__ fbsk, const uint64_t* __restric
       if (!__any_sync(0xffffffffu, need[i] != 0)) continue;
       const uint32_t a = at[i];
       const uint32_t par = n_exec & 1u;
+      if (kTKey) stage_key_to_tmem(n_exec);   // this step's key: shared-memory stage -> tensor memory (needed ~7k cycles from here)
       n_exec++;
-      if (!__any_sync(0xffffffffu, (a & 0x8000u) != 0)) {
-        mbar_wait(full_bar, par);
-        release_stage(i);
+      if (!__any_sync(0xffffffffu, (a & 0x8000u) != 0)) {   // this sample skips the step but takes part in the hand-over
+        if (kTKey) {
+          const int nj = next_needed(i);
+          mbar_wait(tkey_bar, par);
+          if (tid == 0 && nj < kLweN) issue_ggsw(nj);
+          mac_done();
+        } else {
+          mbar_wait(full_bar, par);
+          release_stage(i);
+        }
         continue;
       }
       // phase A + forward pass 1, interleaved
@@ -216,16 +317,32 @@ blind_rotate_fused_kernel(const c2* __restrict__ fbsk, const uint64_t* __restric
       bar_sync(bar_id, 64);
       // forward pass 2, Fourier MAC, inverse pass 1: block by block
       fft32_fwd_s12(xr, xi);
-      mbar_wait(full_bar, par);
-      mid_block<0>(xr, xi, b_own, b_in);
-      mid_block<1>(xr, xi, b_own, b_in);
-      mid_block<2>(xr, xi, b_own, b_in);
-      mid_block<3>(xr, xi, b_own, b_in);
-      release_stage(i);
+      int nj = kLweN;
+      if (kTKey) {
+        nj = next_needed(i);
+        mbar_wait(tkey_bar, par);
+        tmem_fence_after();
+        if (tid == 0 && nj < kLweN) issue_ggsw(nj);
+        uint32_t ka[32], kb[32];
+        tmem_ld32_issue(tkey, ka);
+        mid_block_tmem<0>(xr, xi, tkey, ka, kb);
+        mid_block_tmem<1>(xr, xi, tkey, ka, kb);
+        mid_block_tmem<2>(xr, xi, tkey, ka, kb);
+        mid_block_tmem<3>(xr, xi, tkey, ka, kb);
+        mac_done();
+      } else {
+        mbar_wait(full_bar, par);
+        mid_block<0>(xr, xi, b_own, b_in);
+        mid_block<1>(xr, xi, b_own, b_in);
+        mid_block<2>(xr, xi, b_own, b_in);
+        mid_block<3>(xr, xi, b_own, b_in);
+        release_stage(i);
+      }
       fft32_inv_s45(xr, xi);
       inv_twiddle_inplace(xr, xi, tab_i, k1);
       row_store(xr, plane + pp * kHalfN, k1);
       bar_sync(bar_id, 64);
+
       col_load_brev(xr, plane + w * kHalfN, lane);
       bar_sync(bar_id, 64);
       row_store(xi, plane + pp * kHalfN, k1);
@@ -273,11 +390,21 @@ static cudaError_t launch_fused_s(const c2* fbsk, const uint64_t* small, const u
   return cudaGetLastError();
 }
 
-cudaError_t launch_blind_rotate_fused(const c2* fbsk, const uint64_t* small, const uint64_t* luts, const uint32_t* lut_idx, uint64_t* out,
-                                      const int32_t* out_rows, const c2* tabs, int count, int variant, cudaStream_t st) {
+cudaError_t launch_blind_rotate_fused(const c2* fbsk, const c2* fbsk_lm, const uint64_t* small, const uint64_t* luts, const uint32_t* lut_idx,
+                                      uint64_t* out, const int32_t* out_rows, const c2* tabs, int count, int variant, cudaStream_t st) {
   if (count <= 0) return cudaSuccess;
-  if (variant & 1) return launch_fused_s<4, 1>(fbsk, small, luts, lut_idx, out, out_rows, tabs, count, st);
-  return launch_fused_s<4, 0>(fbsk, small, luts, lut_idx, out, out_rows, tabs, count, st);
+  switch (variant & 3) {
+    case 0: return launch_fused_s<4, 0>(fbsk, small, luts, lut_idx, out, out_rows, tabs, count, st);
+    case 1: return launch_fused_s<4, 1>(fbsk, small, luts, lut_idx, out, out_rows, tabs, count, st);
+    case 2: return launch_fused_s<4, 2>(fbsk_lm, small, luts, lut_idx, out, out_rows, tabs, count, st);
+    default: return launch_fused_s<4, 3>(fbsk_lm, small, luts, lut_idx, out, out_rows, tabs, count, st);
+  }
+}
+
+cudaError_t launch_fbsk_lane_major(const c2* fbsk, c2* fbsk_lm, cudaStream_t st) {
+  const size_t n = (size_t)kLweN * 4096;
+  fbsk_lm_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(fbsk, fbsk_lm);
+  return cudaGetLastError();
 }
 
 }  // namespace fb

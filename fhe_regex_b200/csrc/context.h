@@ -36,6 +36,7 @@ struct fb_ctx {
   // keys
   uint8_t* d_kb = nullptr;     // byte planes of the KSK for the tensor-core keyswitch
   fb::c2* d_fbsk = nullptr;
+  fb::c2* d_fbsk_lm = nullptr; // the same key in the lane-major order of the tensor-memory MAC (br_fused.cu::fbsk_lm_kernel)
   fb::c2* d_tabs = nullptr;
   fb::c2* d_wtab = nullptr;    // table of the latency blind rotation (inside the d_tabs allocation)
   fb::c2* d_dtab = nullptr;    // table of the cluster blind rotation (inside the d_tabs allocation)

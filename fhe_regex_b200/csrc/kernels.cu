@@ -321,7 +321,7 @@ double fp64_peak_flops_per_launch(int ctas) { return (double)ctas * 256.0 * 8.0 
 int br_samples_per_cta() { return 4; }
 
 size_t br_smem_bytes(int S) {
-  return (size_t)kGgswBytes + (size_t)S * 32768 + 2 * kTabEntries * 32 * sizeof(c2) + (size_t)S * 768 * sizeof(uint16_t) + 768 + 16 + 16;
+  return (size_t)kGgswBytes + (size_t)S * 32768 + 2 * kTabEntries * 32 * sizeof(c2) + (size_t)S * 768 * sizeof(uint16_t) + 768 + 16 + 32;
 }
 
 cudaError_t launch_bsk_convert(const uint64_t* bsk_std, c2* fbsk, const c2* tabs, cudaStream_t st) {
