@@ -267,7 +267,7 @@ int fb_run_blind_rotate(fb_ctx* ctx, const uint64_t* d_small, const uint64_t* d_
     const int head = (tail > 0 && tail <= narrow_max) ? count - tail : count;
     // the fused body is built for 4 PBS per SM: batches that do not fill the GPU at that width keep the phase-by-phase body
     const bool fused = ctx->br_variant >= 1 && head > 3 * (q / fb::br_samples_per_cta());
-    e = fused ? fb::launch_blind_rotate_fused(ctx->d_fbsk, ctx->d_fbsk_lm, d_small, d_luts, d_lut_idx, d_out, d_out_rows, ctx->d_tabs, head, ctx->br_variant - 1, ctx->stream)
+    e = fused ? fb::launch_blind_rotate_fused(ctx->d_fbsk, ctx->d_fbsk_lm, d_small, d_luts, d_lut_idx, d_out, d_out_rows, ctx->d_tabs, head, ctx->br_variant - 1, ctx->br_stagger, ctx->stream)
               : fb::launch_blind_rotate(ctx->d_fbsk, d_small, d_luts, d_lut_idx, d_out, d_out_rows, ctx->d_tabs, head, ctx->stream);
     if (e == cudaSuccess && head < count)
       e = narrow(d_small + (size_t)head * FB_LWE_SMALL_WORDS, d_lut_idx + head, d_out_rows ? d_out : d_out + (size_t)head * FB_LWE_BIG_WORDS,
@@ -331,6 +331,7 @@ const OptionDesc kOptions[] = {
     {"wide_prefetch", 0, 4},                // latency kernel: GGSW groups fetched before the pre-MAC barrier
     {"plan_reference_shaped", 0, 1},        // 1: evaluate every variant the reference enumerates (no absorption)
     {"plan_timing", 0, 1},                  // 1: planner phase times on stderr
+    {"br_stagger", 0, 100000},              // fused throughput kernel: start skew between the samples of a CTA, cycles per sample index
 };
 int64_t* option_slot(fb_ctx* ctx, const char* name, int64_t& shadow, int& which) {
   for (int i = 0; i < (int)(sizeof(kOptions) / sizeof(kOptions[0])); i++)
@@ -344,6 +345,7 @@ int64_t* option_slot(fb_ctx* ctx, const char* name, int64_t& shadow, int& which)
         case 4: shadow = ctx->wide_prefetch; break;
         case 5: shadow = ctx->plan_absorb ? 0 : 1; break;
         case 6: shadow = ctx->plan_timing ? 1 : 0; break;
+        case 7: shadow = ctx->br_stagger; break;
       }
       return &shadow;
     }
@@ -374,6 +376,7 @@ extern "C" int fb_set_option(fb_ctx* ctx, const char* name, int64_t value) {
     case 4: ctx->wide_prefetch = (int)value; break;
     case 5: ctx->plan_absorb = value == 0; break;
     case 6: ctx->plan_timing = value != 0; break;
+    case 7: ctx->br_stagger = (int)value; break;
   }
   return FB_OK;
 }

@@ -136,7 +136,7 @@ template <int S, int V>
 __global__ void __launch_bounds__(64 * S, 1)
 blind_rotate_fused_kernel(const c2* __restrict__ fbsk, const uint64_t* __restrict__ small, const uint64_t* __restrict__ luts,
                           const uint32_t* __restrict__ lut_idx, uint64_t* __restrict__ out, const int32_t* __restrict__ out_rows,
-                          const c2* __restrict__ tabs_g, int count) {
+                          const c2* __restrict__ tabs_g, int count, int stagger) {
   static_assert(2 * S <= 32, "64 TMEM columns per warp, 8 warps per lane quarter");
   extern __shared__ __align__(128) unsigned char smem[];
   c2* stage = reinterpret_cast<c2*>(smem);                                             // [2][2][1024]
@@ -281,6 +281,12 @@ blind_rotate_fused_kernel(const c2* __restrict__ fbsk, const uint64_t* __restric
     }
     __syncwarp();
 
+    // optional start skew between the samples of a CTA (cycles per sample index): a few hundred cycles keep every warp
+    // inside the same instruction-cache window while one sample's shared-memory stores fall into another's arithmetic
+    if (stagger > 0 && s > 0) {
+      const long long t0 = clock64();
+      while (clock64() - t0 < (long long)stagger * s) {}
+    }
     double xr[32], xi[32];
     const int pp = lane >> 4, k1 = 16 * w + (lane & 15);
     const c2* b_own = stage + ((size_t)(pp * 2 + pp) * kHalfN + k1);
@@ -377,7 +383,7 @@ blind_rotate_fused_kernel(const c2* __restrict__ fbsk, const uint64_t* __restric
 
 template <int S, int V>
 static cudaError_t launch_fused_s(const c2* fbsk, const uint64_t* small, const uint64_t* luts, const uint32_t* lut_idx, uint64_t* out,
-                                  const int32_t* out_rows, const c2* tabs, int count, cudaStream_t st) {
+                                  const int32_t* out_rows, const c2* tabs, int count, int stagger, cudaStream_t st) {
   const size_t smem = br_smem_bytes(S);
   static PerDeviceOnce once;
   bool& configured = *once.slot();
@@ -386,18 +392,18 @@ static cudaError_t launch_fused_s(const c2* fbsk, const uint64_t* small, const u
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  blind_rotate_fused_kernel<S, V><<<(count + S - 1) / S, 64 * S, smem, st>>>(fbsk, small, luts, lut_idx, out, out_rows, tabs, count);
+  blind_rotate_fused_kernel<S, V><<<(count + S - 1) / S, 64 * S, smem, st>>>(fbsk, small, luts, lut_idx, out, out_rows, tabs, count, stagger);
   return cudaGetLastError();
 }
 
 cudaError_t launch_blind_rotate_fused(const c2* fbsk, const c2* fbsk_lm, const uint64_t* small, const uint64_t* luts, const uint32_t* lut_idx,
-                                      uint64_t* out, const int32_t* out_rows, const c2* tabs, int count, int variant, cudaStream_t st) {
+                                      uint64_t* out, const int32_t* out_rows, const c2* tabs, int count, int variant, int stagger, cudaStream_t st) {
   if (count <= 0) return cudaSuccess;
   switch (variant & 3) {
-    case 0: return launch_fused_s<4, 0>(fbsk, small, luts, lut_idx, out, out_rows, tabs, count, st);
-    case 1: return launch_fused_s<4, 1>(fbsk, small, luts, lut_idx, out, out_rows, tabs, count, st);
-    case 2: return launch_fused_s<4, 2>(fbsk_lm, small, luts, lut_idx, out, out_rows, tabs, count, st);
-    default: return launch_fused_s<4, 3>(fbsk_lm, small, luts, lut_idx, out, out_rows, tabs, count, st);
+    case 0: return launch_fused_s<4, 0>(fbsk, small, luts, lut_idx, out, out_rows, tabs, count, stagger, st);
+    case 1: return launch_fused_s<4, 1>(fbsk, small, luts, lut_idx, out, out_rows, tabs, count, stagger, st);
+    case 2: return launch_fused_s<4, 2>(fbsk_lm, small, luts, lut_idx, out, out_rows, tabs, count, stagger, st);
+    default: return launch_fused_s<4, 3>(fbsk_lm, small, luts, lut_idx, out, out_rows, tabs, count, stagger, st);
   }
 }
 
