@@ -54,3 +54,88 @@ def test_sharded_match_world2_gloo(tmp_path):
     assert total == 1000
     for (got, exp), (content, pattern) in zip(results, CASES):
         assert got == exp, (content, pattern)
+
+
+# ---- the level-sharded collective match (fb_has_match_dist, regex_api.cu run_plan dist) on CPU -----------------------
+# Same partition (slice r of every level = [n r / W, n (r + 1) / W), comm.cu::fb_comm_slice) and the same exchange pattern
+# (every rank holds the whole arena; after a level each rank contributes its slice of the level's output rows), with rows
+# holding plaintext messages instead of ciphertexts and gloo instead of NCCL.  The plan is the library's own
+# (fb_plan_export); a PBS is its LUT (decoded from fb_regex_lut_table), a linear combination is integer arithmetic.
+DIST_CASES = CASES + [("xabbcxabbbbcxx", "/ab{2,4}c/"), ("x" * 40 + "aabc" + "x" * 20, "/a+b?c/"), ("abab", "/^(ab|c)+$/"), ("", "/^$/")]
+
+
+def _dist_level_worker(rank, world, port, out_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import numpy as np
+    import fhe_regex_b200 as fb
+    from oracle import regex_plain as rp
+    luts = fb.regex_lut_table()
+    # f(x) of LUT id: the accumulator holds f(x) << 59 on the box of x (128 coefficients, centred on 128 x)
+    lut_f = np.array([[int(luts[i][128 * x] >> np.uint64(59)) for x in range(16)] for i in range(luts.shape[0])], dtype=np.int64)
+    results = []
+    for content, pattern in DIST_CASES:
+        for ref_shaped in (False, True):
+            plan = fb.plan_export(pattern, len(content), reference_shaped=ref_shaped)
+            if plan["result_kind"] < 2:
+                results.append((plan["result_kind"], rp.has_match(content, pattern)))
+                continue
+            arena = torch.zeros(plan["n_rows"], dtype=torch.int64)
+            blocks = torch.tensor([(ord(c) >> (2 * b)) & 3 for c in content for b in range(4)], dtype=torch.int64)
+            # content: rank r "uploads" slice r, the rest arrives through the exchange
+            n_in = blocks.numel()
+            lo, hi = n_in * rank // world, n_in * (rank + 1) // world
+            arena[lo:hi] = blocks[lo:hi]
+            _exchange(arena, 0, n_in, rank, world)
+            for lv in plan["levels"]:
+                for o, row in enumerate(lv["lin_out_rows"]):
+                    t0, t1 = int(lv["lin_term_off"][o]), int(lv["lin_term_off"][o + 1])
+                    v = int(lv["lin_const"][o] >> np.uint64(59))
+                    for t in range(t0, t1):
+                        v += int(lv["lin_coef"][t]) * int(arena[int(lv["lin_term_rows"][t])])
+                    arena[int(row)] = v
+                n = len(lv["in_rows"])
+                lo, hi = n * rank // world, n * (rank + 1) // world
+                base = lv["out_row_base"]
+                outs = []
+                for b in range(lo, hi):
+                    x = int(arena[int(lv["in_rows"][b])])
+                    assert 0 <= x <= 15, "PBS input outside the message space"
+                    outs.append(int(lut_f[int(lv["lut_idx"][b]), x]))
+                arena[base + lo: base + hi] = torch.tensor(outs, dtype=torch.int64)
+                arena[base: base + lo] = -99          # rows this rank did not compute: must come from the exchange
+                arena[base + hi: base + n] = -99
+                _exchange(arena, base, n, rank, world)
+            results.append((int(arena[plan["result_row"]]), rp.has_match(content, pattern)))
+    # every rank ends with the same result
+    mine = torch.tensor([r[0] for r in results], dtype=torch.int64)
+    allr = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(allr, mine)
+    same = all(bool((a == mine).all()) for a in allr)
+    dist.barrier()
+    if rank == 0:
+        with open(out_path, "w") as f:
+            f.write(repr((results, same)))
+    dist.destroy_process_group()
+
+
+def _exchange(arena, base, n, rank, world):
+    """in-place exchange of row slices: one broadcast per non-empty slice (comm.cu::fb_comm_exchange_rows)"""
+    for root in range(world):
+        lo, hi = n * root // world, n * (root + 1) // world
+        if hi > lo:
+            buf = arena[base + lo: base + hi].clone()
+            dist.broadcast(buf, root)
+            arena[base + lo: base + hi] = buf
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_level_sharded_match_gloo(tmp_path, world):
+    out = str(tmp_path / "res.txt")
+    mp.spawn(_dist_level_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    results, same = eval(open(out).read())
+    assert same
+    assert len(results) == 2 * len(DIST_CASES)
+    for k, (got, exp) in enumerate(results):
+        assert got == exp, DIST_CASES[k // 2]
