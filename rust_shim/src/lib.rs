@@ -40,6 +40,11 @@ extern "C" {
     fn fb_ctx_destroy(ctx: *mut FbCtx);
     fn fb_last_error(ctx: *const FbCtx) -> *const c_char;
     fn fb_load_server_key_raw(ctx: *mut FbCtx, h_ksk: *const u64, h_bsk_std: *const u64) -> c_int;
+    fn fb_load_server_key_bincode(ctx: *mut FbCtx, buf: *const u8, len: usize) -> c_int;
+    fn fb_comm_unique_id(id: *mut u8) -> c_int;
+    fn fb_comm_init(ctx: *mut FbCtx, id: *const u8, rank: c_int, world: c_int) -> c_int;
+    fn fb_has_match_dist(ctx: *mut FbCtx, h_content: *const u64, n_chars: usize, pattern: *const c_char, h_out: *mut u64,
+                         stats: *mut FbMatchStats) -> c_int;
     fn fb_has_match(ctx: *mut FbCtx, h_content: *const u64, n_chars: usize, pattern: *const c_char, h_out: *mut u64,
                     stats: *mut FbMatchStats) -> c_int;
     fn fb_has_match_shard(ctx: *mut FbCtx, h_content: *const u64, n_chars: usize, pattern: *const c_char, rank: c_int,
@@ -77,6 +82,48 @@ impl B200ServerKey {
     }
 }
 
+impl B200ServerKey {
+    /// From the reference's own keygen output (`gen_keys()` ciphertext.rs:42-45, `ServerKey::new(&client_key)` engine.rs:252):
+    /// tfhe-rs 0.2.0 keeps the bootstrapping key in the Fourier domain only and serializes it in a plan-independent natural
+    /// frequency order, which is the library's resident layout (fhe_regex_b200/csrc/wire.cpp).
+    pub fn new(device: i32, sk: &tfhe::integer::ServerKey) -> Result<Self> {
+        let blob = bincode::serialize(sk)?;
+        let mut ctx = std::ptr::null_mut();
+        if unsafe { fb_ctx_create(&mut ctx, device) } != 0 {
+            bail!("libfhe_b200: {} (no CPU fallback)", last_error(std::ptr::null()));
+        }
+        if unsafe { fb_load_server_key_bincode(ctx, blob.as_ptr(), blob.len()) } != 0 {
+            let msg = last_error(ctx);
+            unsafe { fb_ctx_destroy(ctx) };
+            bail!("libfhe_b200: {msg}");
+        }
+        Ok(Self { ctx })
+    }
+
+    /// Join the NCCL communicator of `id` (128 bytes from `comm_unique_id()` on rank 0, handed over by the host's own means).
+    pub fn comm_init(&self, id: &[u8; 128], rank: i32, world: i32) -> Result<()> {
+        check(self.ctx, unsafe { fb_comm_init(self.ctx, id.as_ptr(), rank, world) })
+    }
+}
+
+pub fn comm_unique_id() -> Result<[u8; 128]> {
+    let mut id = [0u8; 128];
+    if unsafe { fb_comm_unique_id(id.as_mut_ptr()) } != 0 {
+        bail!("libfhe_b200: NCCL unavailable");
+    }
+    Ok(id)
+}
+
+/// has_match across the communicator (collective: every rank calls it with the same content and pattern, every rank gets
+/// the result): every PBS level of the plan is cut into `world` slices exchanged over NVLink inside the library.
+pub fn has_match_dist_flat(sk: &B200ServerKey, content: &[u64], n_chars: usize, pattern: &str) -> Result<Vec<u64>> {
+    let mut out = vec![0u64; FB_RADIX_BLOCKS * FB_LWE_BIG_WORDS];
+    let pat = CString::new(pattern)?;
+    let rc = unsafe { fb_has_match_dist(sk.ctx, content.as_ptr(), n_chars, pat.as_ptr(), out.as_mut_ptr(), std::ptr::null_mut()) };
+    check(sk.ctx, rc)?;
+    Ok(out)
+}
+
 impl Drop for B200ServerKey {
     fn drop(&mut self) {
         unsafe { fb_ctx_destroy(self.ctx) }
@@ -112,7 +159,9 @@ pub fn has_match_flat(sk: &B200ServerKey, content: &[u64], n_chars: usize, patte
     Ok((out, stats))
 }
 
-/// One rank's share (start offsets i with i % world == rank) of a match sharded over `world` GPUs.
+/// One rank's share of a match sharded over `world` GPUs without NCCL: the rank-th contiguous slice of the final OR's operands
+/// after global absorption (reference-shaped plan: the variants of start offsets i % world == rank).  Gather the first 2049
+/// words of every rank's result and finish with `or_fold`.
 pub fn has_match_shard_flat(sk: &B200ServerKey, content: &[u64], n_chars: usize, pattern: &str, rank: i32, world: i32) -> Result<Vec<u64>> {
     let mut out = vec![0u64; FB_RADIX_BLOCKS * FB_LWE_BIG_WORDS];
     let pat = CString::new(pattern)?;
