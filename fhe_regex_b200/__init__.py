@@ -88,6 +88,7 @@ def lib():
     L.fb_plan_stats.argtypes = [C.c_char_p, sz, C.c_uint32, C.POINTER(MatchStats)]
     L.fb_plan_level_widths.argtypes = [C.c_char_p, sz, C.c_int, C.c_int, C.c_uint32, vp, sz]
     L.fb_plan_eval_plain.argtypes = [C.c_char_p, vp, sz, C.c_int, C.c_int, C.c_uint32, C.POINTER(C.c_int)]
+    L.fb_keygen_server_gpu.argtypes = [vp, vp, vp, C.c_uint64, vp, vp]
     L.fb_load_server_key_fourier.argtypes = [vp, vp, vp]
     L.fb_load_server_key_bincode.argtypes = [vp, vp, sz]
     L.fb_server_key_bincode_size.restype = sz
@@ -353,7 +354,7 @@ class ServerKey:
     """The server key resident on one B200 (KSK + Fourier BSK in HBM) plus the evaluation context."""
 
     def __init__(self, ksk: np.ndarray = None, bsk_std: np.ndarray = None, device: int = 0, *, fourier_bsk: np.ndarray = None,
-                 bincode: bytes = None):
+                 bincode: bytes = None, keygen_from: "ClientKey" = None, seed: int = 0, keep_generated: bool = False):
         """ksk + bsk_std: the two tfhe-rs containers in the standard domain (fb_load_server_key_raw);
         ksk + fourier_bsk: the Fourier key in tfhe-rs's serialized order (fb_load_server_key_fourier);
         bincode: a serialized tfhe::integer::ServerKey (fb_load_server_key_bincode)."""
@@ -364,6 +365,14 @@ class ServerKey:
             msg = L.fb_last_error(None).decode()
             self._h = None
             raise FbError(rc, msg)
+        if keygen_from is not None:   # ServerKey::new(&client_key) on the GPU (fb_keygen_server_gpu)
+            self.generated = None
+            if keep_generated:
+                self.generated = (np.empty((2048, 5, 743), dtype=np.uint64), np.empty((742, 1, 2, 2, 2048), dtype=np.uint64))
+            self._check(L.fb_keygen_server_gpu(self._h, _p(keygen_from.big), _p(keygen_from.small), seed,
+                                               _p(self.generated[0]) if keep_generated else None,
+                                               _p(self.generated[1]) if keep_generated else None))
+            return
         if bincode is not None:
             buf = np.frombuffer(bincode, dtype=np.uint8)
             self._check(L.fb_load_server_key_bincode(self._h, _p(buf), buf.size))

@@ -4,7 +4,7 @@ import logging
 import os
 import sys
 
-from . import ClientKey, ServerKey, encrypt_str, has_match, keygen_server_raw, parse
+from . import ClientKey, ServerKey, encrypt_str, has_match, parse
 
 
 def main(argv):
@@ -16,8 +16,7 @@ def main(argv):
     logging.info("parsed: %s", parse(pattern))                                  # main.rs:17-20 (raises on a parse error)
     here = os.path.dirname(os.path.abspath(__file__))
     ck = ClientKey.load(os.path.join(here, "..", "tests", "golden", "client_key"))   # fixture secret key instead of fresh keygen
-    ksk, bsk = keygen_server_raw(ck, seed=0)
-    sk = ServerKey(ksk, bsk)
+    sk = ServerKey(keygen_from=ck, seed=0)                                      # ServerKey::new(&client_key), on the GPU
     logging.info("encrypting content..")
     ct = encrypt_str(ck, content)
     logging.info("applying regex..")

@@ -149,23 +149,36 @@ extern "C" int fb_load_server_key_bincode(fb_ctx* ctx, const uint8_t* buf, size_
   return fb_load_server_key_fourier(ctx, ksk.data(), fbsk.data());
 }
 
+// both keys already in device memory (standard domain): byte planes, Fourier transform, lane-major copy
+int fb_install_server_key_device(fb_ctx* ctx, uint64_t* d_ksk, uint64_t* d_bsk_std) {
+  if (!ctx->d_fbsk) FB_CUDA(ctx, cudaMalloc(&ctx->d_fbsk, (size_t)fb::kLweN * 4 * fb::kHalfN * sizeof(c2)));
+  if (!ctx->d_fbsk_lm) FB_CUDA(ctx, cudaMalloc(&ctx->d_fbsk_lm, (size_t)fb::kLweN * 4 * fb::kHalfN * sizeof(c2)));
+  if (!ctx->d_kb) FB_CUDA(ctx, cudaMalloc(&ctx->d_kb, fb::ks_key_bytes()));
+  cudaError_t e = fb::launch_ksk_bytes(d_ksk, ctx->d_kb, ctx->stream);
+  if (e == cudaSuccess) e = fb::launch_bsk_convert(d_bsk_std, ctx->d_fbsk, ctx->d_tabs, ctx->stream);
+  if (e == cudaSuccess) e = fb::launch_fbsk_lane_major(ctx->d_fbsk, ctx->d_fbsk_lm, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) return fb_cuda_fail(ctx, e, "key conversion (byte planes / Fourier transform)");
+  ctx->have_key = true;
+  return FB_OK;
+}
+
 extern "C" int fb_load_server_key_raw(fb_ctx* ctx, const uint64_t* h_ksk, const uint64_t* h_bsk_std) {
   if (!ctx || !h_ksk || !h_bsk_std) return fb_fail(ctx, FB_ERR_ARG, "null argument");
   FB_CUDA(ctx, cudaSetDevice(ctx->device));
-  {
-    int rc = upload_ksk(ctx, h_ksk);
-    if (rc != FB_OK) return rc;
+  uint64_t *d_ksk = nullptr, *d_std = nullptr;   // staging copies of the u64 keys; only their converted forms stay resident
+  FB_CUDA(ctx, cudaMalloc(&d_ksk, FB_KSK_WORDS * sizeof(uint64_t)));
+  if (cudaMalloc(&d_std, FB_BSK_WORDS * sizeof(uint64_t)) != cudaSuccess) {
+    cudaFree(d_ksk);
+    return fb_fail(ctx, FB_ERR_CUDA, "cudaMalloc of the key staging buffer failed");
   }
-  uint64_t* d_std = nullptr;
-  FB_CUDA(ctx, cudaMalloc(&d_std, FB_BSK_WORDS * sizeof(uint64_t)));
-  cudaError_t e = cudaMemcpyAsync(d_std, h_bsk_std, FB_BSK_WORDS * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
-  if (e == cudaSuccess) e = fb::launch_bsk_convert(d_std, ctx->d_fbsk, ctx->d_tabs, ctx->stream);
-  if (e == cudaSuccess) e = fb::launch_fbsk_lane_major(ctx->d_fbsk, ctx->d_fbsk_lm, ctx->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaError_t e = cudaMemcpyAsync(d_ksk, h_ksk, FB_KSK_WORDS * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_std, h_bsk_std, FB_BSK_WORDS * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
+  int rc = e == cudaSuccess ? fb_install_server_key_device(ctx, d_ksk, d_std) : fb_cuda_fail(ctx, e, "key upload");
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_ksk);
   cudaFree(d_std);
-  if (e != cudaSuccess) return fb_cuda_fail(ctx, e, "key upload / Fourier conversion");
-  ctx->have_key = true;
-  return FB_OK;
+  return rc;
 }
 
 extern "C" int fb_get_fourier_bsk(fb_ctx* ctx, double* h_out) {

@@ -86,6 +86,9 @@ int fb_reserve(fb_ctx* ctx, fb_devbuf& b, size_t bytes);
 void fb_comm_slice(size_t n, int r, int world, size_t* lo, size_t* hi);
 int fb_comm_exchange_rows(fb_ctx* ctx, uint64_t* d_rows, size_t n, size_t row_words);
 
+// api.cu: both keys already in device memory (standard domain) -> resident forms
+int fb_install_server_key_device(fb_ctx* ctx, uint64_t* d_ksk, uint64_t* d_bsk_std);
+
 // timed launches on ctx->stream (timing is a no-op unless enabled)
 int fb_run_keyswitch(fb_ctx* ctx, const uint64_t* d_in, const int32_t* d_in_rows, uint64_t* d_small, int count);
 int fb_run_blind_rotate(fb_ctx* ctx, const uint64_t* d_small, const uint64_t* d_luts, const uint32_t* d_lut_idx,

@@ -90,6 +90,13 @@ int fb_load_server_key_fourier(fb_ctx* ctx, const uint64_t* h_ksk, const double*
  * the blob a maintainer gets from the value engine.rs:252 / ciphertext.rs:44 produce.  FB_ERR_FORMAT if any length or
  * parameter differs. */
 int fb_load_server_key_bincode(fb_ctx* ctx, const uint8_t* buf, size_t len);
+/* `ServerKey::new(&client_key)` / `gen_keys_radix` (engine.rs:252, ciphertext.rs:44) ON the GPU: both keys are generated in
+ * device memory from the client's secret key bits (KSK rows and GGSW rows encrypted by CUDA kernels, counter-based PRNG seeded by
+ * `seed`, Box-Muller noise with the parameter set's standard deviations) and installed in this context; h_ksk / h_bsk_std, if
+ * not NULL, receive copies in the layouts of fb_load_server_key_raw.  Statistically equivalent to, not bit-identical with, a
+ * tfhe-rs key.  Milliseconds instead of the seconds of the CPU keygen. */
+int fb_keygen_server_gpu(fb_ctx* ctx, const uint64_t* h_big_key, const uint64_t* h_small_key, uint64_t seed, uint64_t* h_ksk,
+                         uint64_t* h_bsk_std);
 /* read back the Fourier BSK ([742][2][2][1024] complex f64, natural frequency order) -- tests only */
 int fb_get_fourier_bsk(fb_ctx* ctx, double* h_out);
 

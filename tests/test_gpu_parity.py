@@ -425,6 +425,72 @@ def test_every_kernel_on_a_small_ragged_case():
     mod.main()
 
 
+def test_server_keygen_on_the_gpu(client_key, fck):
+    """fb_keygen_server_gpu = ServerKey::new(&client_key) (engine.rs:252) in CUDA kernels.  The generated key is checked
+    row by row against the secret keys (plaintexts exact, noise of the parameter set's standard deviations), the keyswitch
+    through it is bit-exact against the oracle run on the downloaded key, and bootstraps / a match decrypt correctly."""
+    sk = fb.ServerKey(keygen_from=fck, seed=11, keep_generated=True)
+    try:
+        ksk, bsk = sk.generated
+        small = fck.small.astype(np.uint64)
+        big = fck.big.astype(np.uint64)
+        with np.errstate(over="ignore"):
+            # KSK row (i, l): phase = body - <mask, s> = big[i] * 2^(64 - 3(l+1)) + e, e ~ N(0, sigma_lwe)
+            phase = ksk[:, :, 742] - (ksk[:, :, :742] * small[None, None, :]).sum(axis=2, dtype=np.uint64)
+            want = big[:, None] << np.array([61, 58, 55, 52, 49], dtype=np.uint64)[None, :]
+            err = (phase - want).view(np.int64).astype(np.float64) / 2.0 ** 64
+        assert np.abs(err).max() < 6 * 7.07e-6 and 0.9 * 7.07e-6 < err.std() < 1.1 * 7.07e-6, (err.std(), np.abs(err).max())
+        assert abs(err.mean()) < 4 * 7.07e-6 / np.sqrt(err.size)
+        # masks are fresh: no two rows share their first words
+        assert len({int(x) for x in ksk[:, :, 0].reshape(-1)}) == 2048 * 5
+        # BSK GGSW rows: B - A * S = plaintext + e, checked exactly (integer negacyclic product) on a few rows
+        ones = np.nonzero(big)[0]
+        for i in (0, 1, 371, 741):
+            for r in (0, 1):
+                A, B = bsk[i, 0, r, 0], bsk[i, 0, r, 1]
+                prod = np.zeros(2048, dtype=np.uint64)
+                with np.errstate(over="ignore"):
+                    for t in ones:
+                        rolled = np.roll(A, t)
+                        rolled[:t] = np.uint64(0) - rolled[:t]
+                        prod += rolled
+                    factor = np.uint64(int(small[i]) << 41)
+                    pt = (np.uint64(0) - factor * big) if r == 0 else np.concatenate([[factor], np.zeros(2047, dtype=np.uint64)]).astype(np.uint64)
+                    e = (B - prod - pt).view(np.int64).astype(np.float64) / 2.0 ** 64
+                assert np.abs(e).max() < 6 * 2.95e-16 and 0.85 * 2.94e-16 < e.std() < 1.15 * 2.94e-16, (i, r, e.std())
+        # keyswitch through the installed key == oracle keyswitch with the downloaded key, bit for bit
+        osk = tfhe.ServerKey(ksk, bsk)
+        msgs = np.arange(16)
+        cts = tfhe.encrypt_batch(client_key, msgs, seed=41)
+        assert (sk.keyswitch(cts) == tfhe.keyswitch(osk, cts)).all()
+        lut = fb.make_lut(lambda x: (5 * x + 7) % 16)
+        out = sk.pbs(cts, lut[None], np.zeros(16, dtype=np.uint32))
+        assert [fck.decrypt_block(c) for c in out] == [(5 * m + 7) % 16 for m in msgs]
+        ph = tfhe.phase_batch(client_key.big, out)
+        errb = tfhe.torus_err(ph, np.array([((5 * m + 7) % 16) << 59 for m in msgs], dtype=np.uint64))
+        assert np.abs(errb).max() < PBS_ERR_MAX
+        assert fck.decrypt(fb.has_match(sk, fb.encrypt_str(fck, "xxabbbcx", seed=2), "/ab{2,4}c/")) == 1
+    finally:
+        sk.close()
+    # a different seed gives a different key
+    sk2 = fb.ServerKey(keygen_from=fck, seed=12, keep_generated=True)
+    assert (sk2.generated[0][0, 0, :8] != ksk[0, 0, :8]).any()
+    sk2.close()
+
+
+def test_demo_entry_point_prints_res(capsys):
+    """`python -m fhe_regex_b200 <content> <pattern>` = the reference's `cargo run -- <content> <pattern>` (src/main.rs:9-23,
+    src/regex/mod.rs:9-19): keygen, encrypt_str, has_match, decrypt, `res: 0|1` on stdout."""
+    from fhe_regex_b200.__main__ import main
+    assert main(["fhe-regex", "abc", "/^abc$/"]) == 0
+    assert capsys.readouterr().out.strip().splitlines()[-1] == "res: 1"
+    assert main(["fhe-regex", "abd", "/^abc$/"]) == 0
+    assert capsys.readouterr().out.strip().splitlines()[-1] == "res: 0"
+    assert main(["fhe-regex", "abc"]) == 2
+    with pytest.raises(fb.ParseError):
+        main(["fhe-regex", "abc", "/a(b/"])
+
+
 def test_has_match_dist_single_rank_communicator(fck, server_key):
     """fb_comm_init + fb_has_match_dist with a communicator of one rank (what a 1-GPU box can run; the multi-rank path is
     exercised by tools/dist_match_check.py under torchrun, profiles/r02_dist_n*.log): same decryption as fb_has_match."""
