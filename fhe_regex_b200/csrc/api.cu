@@ -52,6 +52,7 @@ extern "C" int fb_ctx_create(fb_ctx** out, int device) {
   if (!ctx) return FB_ERR_ARG;
   ctx->device = device;
   ctx->quantum = prop.multiProcessorCount * fb::br_samples_per_cta();
+  ctx->sms = prop.multiProcessorCount;
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete ctx;
     g_create_err = "cudaSetDevice / cudaStreamCreate failed";
@@ -250,7 +251,7 @@ int fb_run_keyswitch(fb_ctx* ctx, const uint64_t* d_in, const int32_t* d_in_rows
   if (rc) return rc;
   fb_event_pair ev;
   bool t = timing_begin(ctx, 0, ev);
-  cudaError_t e = fb::launch_keyswitch_mma(ctx->d_kb, (int8_t*)ctx->digits.p, d_in, d_in_rows, d_small, count, ctx->stream);
+  cudaError_t e = fb::launch_keyswitch_mma(ctx->d_kb, (int8_t*)ctx->digits.p, d_in, d_in_rows, d_small, count, ctx->ks_variant, ctx->sms, ctx->stream);
   timing_end(ctx, t, ev);
   if (e != cudaSuccess) return fb_cuda_fail(ctx, e, "keyswitch_kernel launch");
   ctx->ks.ks_launches++;
@@ -345,6 +346,7 @@ const OptionDesc kOptions[] = {
     {"plan_reference_shaped", 0, 1},        // 1: evaluate every variant the reference enumerates (no absorption)
     {"plan_timing", 0, 1},                  // 1: planner phase times on stderr
     {"br_stagger", 0, 100000},              // fused throughput kernel: start skew between the samples of a CTA, cycles per sample index
+    {"ks_variant", 0, 1},                   // keyswitch GEMM: 0 mma.sync, 1 tcgen05.mma kind::i8 (TMA operands, TMEM accumulators)
 };
 int64_t* option_slot(fb_ctx* ctx, const char* name, int64_t& shadow, int& which) {
   for (int i = 0; i < (int)(sizeof(kOptions) / sizeof(kOptions[0])); i++)
@@ -359,6 +361,7 @@ int64_t* option_slot(fb_ctx* ctx, const char* name, int64_t& shadow, int& which)
         case 5: shadow = ctx->plan_absorb ? 0 : 1; break;
         case 6: shadow = ctx->plan_timing ? 1 : 0; break;
         case 7: shadow = ctx->br_stagger; break;
+        case 8: shadow = ctx->ks_variant; break;
       }
       return &shadow;
     }
@@ -390,6 +393,7 @@ extern "C" int fb_set_option(fb_ctx* ctx, const char* name, int64_t value) {
     case 5: ctx->plan_absorb = value == 0; break;
     case 6: ctx->plan_timing = value != 0; break;
     case 7: ctx->br_stagger = (int)value; break;
+    case 8: ctx->ks_variant = (int)value; break;
   }
   return FB_OK;
 }

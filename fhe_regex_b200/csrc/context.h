@@ -47,6 +47,8 @@ struct fb_ctx {
   int wide_skew = 200;         // latency kernel: cycles one half of the CTA is held back after the MAC (option "wide_skew")
   int wide_prefetch = 3;       // latency kernel: GGSW groups fetched before the pre-MAC barrier (option "wide_prefetch")
   int br_variant = 2;          // throughput blind rotation at 4 PBS per SM: 0 = phase-by-phase body (kernels.cu), 1 = fused body (br_fused.cu), 2 = fused + digits through I2F
+  int ks_variant = 1;          // keyswitch GEMM: 0 = mma.sync (ks_kernels.cu), 1 = tcgen05 (ks_umma.cu) (option "ks_variant")
+  int sms = 148;               // multiprocessors of the device
   int br_stagger = 0;          // fused throughput kernel: start skew between the samples of a CTA, cycles per sample index (option "br_stagger")
   bool plan_absorb = true;     // false: reference-shaped plan (option "plan_reference_shaped" = 1)
   bool plan_timing = false;    // planner phase times on stderr (option "plan_timing")

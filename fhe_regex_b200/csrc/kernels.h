@@ -42,8 +42,9 @@ cudaError_t launch_lincomb(uint64_t* arena, const int32_t* out_rows, const int32
 size_t ks_key_bytes();
 size_t ks_digit_bytes(int count);
 cudaError_t launch_ksk_bytes(const uint64_t* ksk, uint8_t* kb, cudaStream_t st);
+// variant 0: mma.sync GEMM (ks_kernels.cu), 1: tcgen05.mma kind::i8 GEMM with TMA-staged operands and TMEM accumulators (ks_umma.cu)
 cudaError_t launch_keyswitch_mma(const uint8_t* kb, int8_t* dig, const uint64_t* in, const int32_t* in_rows, uint64_t* out, int count,
-                                 cudaStream_t st);
+                                 int variant, int sms, cudaStream_t st);
 cudaError_t launch_fp64_peak(double* sink, int ctas, cudaStream_t st);
 double fp64_peak_flops_per_launch(int ctas);
 int br_samples_per_cta();

@@ -26,7 +26,8 @@ namespace fb {
 constexpr int kKsK = kN * kKsLevels;          // 10240 contraction length
 constexpr int kKsNReal = kSmall * 8;          // 5944 byte-plane columns
 constexpr int KS_BM = 128, KS_BN = 128, KS_BK = 64, KS_STAGES = 4;
-constexpr int kKsNPad = ((kKsNReal + KS_BN - 1) / KS_BN) * KS_BN;  // 6016
+constexpr int kKsNTiles = (kKsNReal + KS_BN - 1) / KS_BN;           // 47 column tiles of the mma.sync GEMM
+constexpr int kKsNPad = 6144;                                       // rows of the byte-plane matrix: a multiple of the 256-wide tcgen05 tile (ks_umma.cu)
 
 size_t ks_key_bytes() { return (size_t)kKsNPad * kKsK; }
 size_t ks_digit_bytes(int count) { return (size_t)((count + KS_BM - 1) / KS_BM) * KS_BM * kKsK; }
@@ -205,19 +206,24 @@ ks_gemm_kernel(const int8_t* __restrict__ dig, const uint8_t* __restrict__ kb, c
 
 // ---- launchers -------------------------------------------------------------------------------------
 cudaError_t launch_ksk_bytes(const uint64_t* ksk, uint8_t* kb, cudaStream_t st) {
-  cudaError_t e = cudaMemsetAsync(kb, 0, ks_key_bytes(), st);  // padding rows 5944..6015
+  cudaError_t e = cudaMemsetAsync(kb, 0, ks_key_bytes(), st);  // padding rows 5944..6143
   if (e != cudaSuccess) return e;
   ksk_bytes_kernel<<<dim3(kKsK / 32, (kSmall + 31) / 32), dim3(32, 8), 0, st>>>(ksk, kb);
   return cudaGetLastError();
 }
 
+cudaError_t launch_keyswitch_umma_gemm(const uint8_t* kb, const int8_t* dig, const uint64_t* in, const int32_t* in_rows, uint64_t* out,
+                                       int count, int sms, cudaStream_t st);   // ks_umma.cu
+
+// variant 0: mma.sync GEMM (this file); 1: tcgen05 GEMM (ks_umma.cu).  Same digits, same key bytes, same result.
 cudaError_t launch_keyswitch_mma(const uint8_t* kb, int8_t* dig, const uint64_t* in, const int32_t* in_rows, uint64_t* out, int count,
-                                 cudaStream_t st) {
+                                 int variant, int sms, cudaStream_t st) {
   if (count <= 0) return cudaSuccess;
   const int mt = (count + KS_BM - 1) / KS_BM;
   ks_decompose_kernel<<<dim3(mt * KS_BM, 2), 256, 0, st>>>(in, in_rows, dig, count, mt * KS_BM);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
+  if (variant == 1) return launch_keyswitch_umma_gemm(kb, dig, in, in_rows, out, count, sms, st);
   constexpr int smem = KS_STAGES * (KS_BM + KS_BN) * KS_BK;  // 65536
   static PerDeviceOnce once;
   bool& configured = *once.slot();
@@ -226,7 +232,7 @@ cudaError_t launch_keyswitch_mma(const uint8_t* kb, int8_t* dig, const uint64_t*
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  ks_gemm_kernel<<<dim3(kKsNPad / KS_BN, mt), 256, smem, st>>>(dig, kb, in, in_rows, out, count);
+  ks_gemm_kernel<<<dim3(kKsNTiles, mt), 256, smem, st>>>(dig, kb, in, in_rows, out, count);
   return cudaGetLastError();
 }
 
