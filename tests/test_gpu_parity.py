@@ -537,3 +537,56 @@ def test_server_key_in_the_references_own_form(client_key, server_key, gpu_key, 
             sk.close()
     with pytest.raises(fb.FbError):
         fb.ServerKey(bincode=blob[:-1])
+
+
+def test_options_are_per_context_and_checked(gpu_key, server_key):
+    """fb_set_option / fb_get_option: defaults, round trip, unknown names and out-of-range values are errors, and a second
+    context keeps its own values"""
+    assert gpu_key.get_option("br_variant") == 2 and gpu_key.get_option("ks_variant") == 1 and gpu_key.get_option("latency_threshold") == 296
+    prev = gpu_key.set_option("latency_threshold", 100)
+    assert prev == 296 and gpu_key.get_option("latency_threshold") == 100
+    other = fb.ServerKey(server_key.ksk, server_key.bsk)
+    try:
+        assert other.get_option("latency_threshold") == 296
+    finally:
+        other.close()
+    gpu_key.set_option("latency_threshold", prev)
+    for name, value in (("no_such_option", 1), ("br_variant", 9), ("ks_variant", -1)):
+        with pytest.raises(fb.FbError):
+            gpu_key.set_option(name, value)
+
+
+def test_keyswitch_variants_agree_bit_for_bit(client_key, server_key, gpu_key):
+    """the tcgen05 GEMM (ks_umma.cu) and the mma.sync GEMM (ks_kernels.cu) are the same exact integer contraction"""
+    rng = np.random.default_rng(3)
+    cts = rng.integers(0, 2 ** 64, size=(300, tfhe.BIG), dtype=np.uint64)      # 300: ragged against both tile heights
+    outs = []
+    for v in (0, 1):
+        prev = gpu_key.set_option("ks_variant", v)
+        outs.append(gpu_key.keyswitch(cts))
+        gpu_key.set_option("ks_variant", prev)
+    assert (outs[0] == outs[1]).all()
+    assert (outs[1][:40] == tfhe.keyswitch(server_key, cts[:40])).all()
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
+def test_throughput_blind_rotation_variants(variant, client_key, server_key, gpu_key, fck):
+    """every body of the throughput blind rotation (phase by phase, fused, fused + I2F digits, + tensor-memory key) on a
+    batch with a ragged last CTA: decrypt-exact, error within the stated bound"""
+    n = 4 * 148 + 3
+    msgs = np.arange(n) % 16
+    base = tfhe.encrypt_batch(client_key, msgs[:64], seed=51)
+    cts = np.ascontiguousarray(np.tile(base, ((n + 63) // 64, 1))[:n])
+    f = lambda x: (9 * x + 4) % 16
+    lut = fb.make_lut(f)
+    prev = (gpu_key.set_option("br_variant", variant), gpu_key.set_latency_threshold(0))
+    try:
+        out = gpu_key.pbs(cts, lut[None], np.zeros(n, dtype=np.uint32))
+    finally:
+        gpu_key.set_option("br_variant", prev[0])
+        gpu_key.set_latency_threshold(prev[1])
+    exp = np.array([f(int(m % 64 % 16)) for m in range(n)], dtype=np.uint64)
+    ph = tfhe.phase_batch(client_key.big, out)
+    err = tfhe.torus_err(ph, exp << np.uint64(59))
+    assert [fck.decrypt_block(out[i]) for i in (0, 1, 63, 64, n - 2, n - 1)] == [int(exp[i]) for i in (0, 1, 63, 64, n - 2, n - 1)]
+    assert np.abs(err).max() < PBS_ERR_MAX and err.std() < PBS_ERR_STD_MAX, (variant, err.std())

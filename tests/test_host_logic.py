@@ -183,3 +183,21 @@ def test_client_glue_against_oracle(client_key):
         fb.encrypt_str(ck, "é")
     for f in (lambda x: x, lambda x: int(x == 3), lambda x: 15 - x):
         assert (fb.make_lut(f) == tfhe.make_lut(f)).all()
+
+
+def test_library_reads_nothing_from_the_environment():
+    """every knob is a per-context option (fb_set_option): no getenv anywhere in the product sources"""
+    csrc = os.path.join(ROOT, "fhe_regex_b200", "csrc")
+    for name in sorted(os.listdir(csrc)):
+        if name.endswith((".cu", ".cpp", ".cuh", ".h")):
+            assert "getenv" not in open(os.path.join(csrc, name)).read(), name
+
+
+def test_product_does_not_touch_the_oracle():
+    """oracle/ is test infrastructure: nothing under fhe_regex_b200/ or include/ imports, links or opens it"""
+    for base in ("fhe_regex_b200", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, base)):
+            for name in files:
+                if name.endswith((".py", ".cu", ".cpp", ".cuh", ".h")):
+                    txt = open(os.path.join(dirpath, name)).read()
+                    assert "from oracle" not in txt and "import oracle" not in txt and "libtfhe_oracle" not in txt and "oracle/" not in txt, name
