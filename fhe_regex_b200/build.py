@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfhe_b200.so")
-SOURCES = ["kernels.cu", "br_fused.cu", "br_wide.cu", "br_duo.cu", "ks_kernels.cu", "ks_umma.cu", "api.cu", "comm.cu", "handles.cu", "keygen.cu", "regex_api.cu", "regex_host.cpp", "client.cpp", "wire.cpp"]
+SOURCES = ["kernels.cu", "br_fused.cu", "br_wide.cu", "br_wide2.cu", "br_duo.cu", "ks_kernels.cu", "ks_umma.cu", "api.cu", "comm.cu", "handles.cu", "keygen.cu", "regex_api.cu", "regex_host.cpp", "client.cpp", "wire.cpp"]
 HEADERS = ["br_core.cuh", "br_tmem.cuh", "br_wide.cuh", "br_duo.cuh", "ptx_sync.cuh", "fft32_gen.h", "kernels.h", "context.h", "regex_host.h", os.path.join("..", "..", "include", "fhe_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -266,10 +266,12 @@ int fb_run_blind_rotate(fb_ctx* ctx, const uint64_t* d_small, const uint64_t* d_
   // (kernels.cu, up to 4 PBS per CTA).  A short tail behind full throughput waves (e.g. 620 = 592 + 28) would
   // cost a whole extra throughput wave: it goes to the latency kernel instead.
   // Narrower still -- at most as many PBS as the device runs CTA pairs -- a PBS gets two SMs (br_duo.cu).
+  // Between one and two waves of SMs (149 .. 296 PBS on a B200) two PBS share a CTA (br_wide2.cu): both waves at once.
   auto narrow = [&](const uint64_t* sm, const uint32_t* li, uint64_t* o, const int32_t* orows, int n) {
-    return (n <= ctx->duo_max)
-               ? fb::launch_blind_rotate_duo(ctx->d_fbsk, sm, d_luts, li, o, orows, ctx->d_dtab, n, ctx->stream)
-               : fb::launch_blind_rotate_wide(ctx->d_fbsk, sm, d_luts, li, o, orows, ctx->d_wtab, n, ctx->wide_skew, ctx->wide_prefetch, ctx->stream);
+    if (n <= ctx->duo_max) return fb::launch_blind_rotate_duo(ctx->d_fbsk, sm, d_luts, li, o, orows, ctx->d_dtab, n, ctx->stream);
+    if (ctx->wide_pair == 2 || (ctx->wide_pair == 1 && n > ctx->sms && n <= 2 * ctx->sms))
+      return fb::launch_blind_rotate_wide2(ctx->d_fbsk, sm, d_luts, li, o, orows, ctx->d_wtab, n, ctx->wide_skew, ctx->wide_pair_prefetch, ctx->wide_pair_offset, ctx->stream);
+    return fb::launch_blind_rotate_wide(ctx->d_fbsk, sm, d_luts, li, o, orows, ctx->d_wtab, n, ctx->wide_skew, ctx->wide_prefetch, ctx->stream);
   };
   const int narrow_max = ctx->wide_max > ctx->duo_max ? ctx->wide_max : ctx->duo_max;
   cudaError_t e;
@@ -347,6 +349,9 @@ const OptionDesc kOptions[] = {
     {"plan_timing", 0, 1},                  // 1: planner phase times on stderr
     {"br_stagger", 0, 100000},              // fused throughput kernel: start skew between the samples of a CTA, cycles per sample index
     {"ks_variant", 0, 1},                   // keyswitch GEMM: 0 mma.sync, 1 tcgen05.mma kind::i8 (TMA operands, TMEM accumulators)
+    {"wide_pair", 0, 2},                    // latency kernel with two PBS per CTA: 0 never, 1 for batches between one and two waves of SMs, 2 for every narrow batch
+    {"wide_pair_prefetch", 0, 2},           // pair kernel: GGSW groups fetched before the pre-MAC barrier
+    {"wide_pair_offset", 0, 100000},        // pair kernel: cycles the second sample of a CTA starts late
 };
 int64_t* option_slot(fb_ctx* ctx, const char* name, int64_t& shadow, int& which) {
   for (int i = 0; i < (int)(sizeof(kOptions) / sizeof(kOptions[0])); i++)
@@ -362,6 +367,9 @@ int64_t* option_slot(fb_ctx* ctx, const char* name, int64_t& shadow, int& which)
         case 6: shadow = ctx->plan_timing ? 1 : 0; break;
         case 7: shadow = ctx->br_stagger; break;
         case 8: shadow = ctx->ks_variant; break;
+        case 9: shadow = ctx->wide_pair; break;
+        case 10: shadow = ctx->wide_pair_prefetch; break;
+        case 11: shadow = ctx->wide_pair_offset; break;
       }
       return &shadow;
     }
@@ -394,6 +402,9 @@ extern "C" int fb_set_option(fb_ctx* ctx, const char* name, int64_t value) {
     case 6: ctx->plan_timing = value != 0; break;
     case 7: ctx->br_stagger = (int)value; break;
     case 8: ctx->ks_variant = (int)value; break;
+    case 9: ctx->wide_pair = (int)value; break;
+    case 10: ctx->wide_pair_prefetch = (int)value; break;
+    case 11: ctx->wide_pair_offset = (int)value; break;
   }
   return FB_OK;
 }

@@ -93,7 +93,7 @@ FB_HD void dft8(c2 (&x)[8]) {
    : (m) == 6 ? 0.92387953251128675613 : 0.98078528040323044913)
 
 // twist by exp(i pi m/16) per register, 8-point DFT, stage-1 twiddle (carries w^t), store
-FB_HD void fwd_stage1_core(c2 (&x)[8], int t, const Tw& tw, c2* out) {
+FB_HD void fwd_stage1_core(c2 (&x)[8], int t, const c2 (&w1f)[8], c2* out) {
 #pragma unroll
   for (int m = 1; m < 8; m++) {
     const double cm = FB_WIDE_C16(m), sm = FB_WIDE_S16(m);
@@ -101,13 +101,14 @@ FB_HD void fwd_stage1_core(c2 (&x)[8], int t, const Tw& tw, c2* out) {
   }
   dft8<false>(x);
 #pragma unroll
-  for (int k = 0; k < 8; k++) out[swz(8 * t + k)] = cmul(x[k], tw.w1f[k]);
+  for (int k = 0; k < 8; k++) out[swz(8 * t + k)] = cmul(x[k], w1f[k]);
 }
+FB_HD void fwd_stage1_core(c2 (&x)[8], int t, const Tw& tw, c2* out) { fwd_stage1_core(x, t, tw.w1f, out); }
 
 // phase A + forward stage 1: digits of (acc X^a - acc) for coefficients j = t + 128 m and j + 1024.
 // own[2m], own[2m+1]: this thread's accumulator words of those coefficients (registers; the thread that rounds
 // coefficient j in phase C is the one that decomposes it here); accp: the shared copy, for the rotated reads
-FB_HD void fwd_stage1(const uint32_t* accp, const uint32_t (&own)[16], uint32_t a, int t, const Tw& tw, c2* out) {
+FB_HD void fwd_stage1(const uint32_t* accp, const uint32_t (&own)[16], uint32_t a, int t, const c2 (&w1f)[8], c2* out) {
   c2 x[8];
 #pragma unroll
   for (int m = 0; m < 8; m++) {
@@ -115,10 +116,13 @@ FB_HD void fwd_stage1(const uint32_t* accp, const uint32_t (&own)[16], uint32_t 
     x[m].x = pbs_digit32(rot_read32(accp, j, a) - own[2 * m]);
     x[m].y = pbs_digit32(rot_read32(accp, j + 1024u, a) - own[2 * m + 1]);
   }
-  fwd_stage1_core(x, t, tw, out);
+  fwd_stage1_core(x, t, w1f, out);
+}
+FB_HD void fwd_stage1(const uint32_t* accp, const uint32_t (&own)[16], uint32_t a, int t, const Tw& tw, c2* out) {
+  fwd_stage1(accp, own, a, t, tw.w1f, out);
 }
 
-FB_HD void fwd_stage2(const c2* in, c2* out, int t, const Tw& tw) {
+FB_HD void fwd_stage2(const c2* in, c2* out, int t, const c2 (&w2f)[7]) {
   const int q = t & 7, p = t >> 3;
   c2 x[8];
 #pragma unroll
@@ -126,8 +130,9 @@ FB_HD void fwd_stage2(const c2* in, c2* out, int t, const Tw& tw) {
   dft8<false>(x);
   out[swz(q + 64 * p)] = x[0];
 #pragma unroll
-  for (int k = 1; k < 8; k++) out[swz(q + 64 * p + 8 * k)] = cmul(x[k], tw.w2f[k - 1]);
+  for (int k = 1; k < 8; k++) out[swz(q + 64 * p + 8 * k)] = cmul(x[k], w2f[k - 1]);
 }
+FB_HD void fwd_stage2(const c2* in, c2* out, int t, const Tw& tw) { fwd_stage2(in, out, t, tw.w2f); }
 
 // stage-3 twiddles depend on p3 = t >> 6 only, which is warp-uniform: compile-time constants behind a uniform branch
 // forward W16^{p3 k} = exp(-i pi p3 k / 8); inverse exp(+i pi p3 k / 8) * w^{-64 (k & 1)} (the per-parity part of
@@ -178,7 +183,7 @@ FB_HD void mac_prefetch(const c2* ggsw, int qo, int t, c2 (&gpre)[4 * (NPRE > 0 
   }
 }
 template <int NPRE>
-FB_HD void mac_inv_stage1(const c2* in0, const c2* in1, const c2* ggsw, const c2* gpre, int qo, int t, const Tw& tw, c2* out) {
+FB_HD void mac_inv_stage1(const c2* in0, const c2* in1, const c2* ggsw, const c2* gpre, int qo, int t, const c2 (&w1i)[7], c2* out) {
   c2 o[8];
   const c2* g0 = ggsw + (size_t)(0 * 2 + qo) * kHalfN;
   const c2* g1 = ggsw + (size_t)(1 * 2 + qo) * kHalfN;
@@ -198,7 +203,11 @@ FB_HD void mac_inv_stage1(const c2* in0, const c2* in1, const c2* ggsw, const c2
   dft8<true>(o);
   out[swz(8 * t)] = o[0];
 #pragma unroll
-  for (int k = 1; k < 8; k++) out[swz(8 * t + k)] = cmul(o[k], tw.w1i[k - 1]);
+  for (int k = 1; k < 8; k++) out[swz(8 * t + k)] = cmul(o[k], w1i[k - 1]);
+}
+template <int NPRE>
+FB_HD void mac_inv_stage1(const c2* in0, const c2* in1, const c2* ggsw, const c2* gpre, int qo, int t, const Tw& tw, c2* out) {
+  mac_inv_stage1<NPRE>(in0, in1, ggsw, gpre, qo, t, tw.w1i, out);
 }
 
 // pointwise product variant for the negacyclic-product test (one polynomial, spectrum b in natural order)
@@ -217,15 +226,16 @@ FB_HD void mul_inv_stage1(const c2* in0, const c2* spec, int t, const Tw& tw, c2
   for (int k = 1; k < 8; k++) out[swz(8 * t + k)] = cmul(o[k], tw.w1i[k - 1]);
 }
 
-FB_HD void inv_stage2(const c2* in, c2* out, int t, const Tw& tw) {
+FB_HD void inv_stage2(const c2* in, c2* out, int t, const c2 (&w2i)[8]) {
   const int q = t & 7, p = t >> 3;
   c2 x[8];
 #pragma unroll
   for (int r = 0; r < 8; r++) x[r] = in[swz(q + 8 * p + 128 * r)];
   dft8<true>(x);
 #pragma unroll
-  for (int k = 0; k < 8; k++) out[swz(q + 64 * p + 8 * k)] = cmul(x[k], tw.w2i[k]);
+  for (int k = 0; k < 8; k++) out[swz(q + 64 * p + 8 * k)] = cmul(x[k], w2i[k]);
 }
+FB_HD void inv_stage2(const c2* in, c2* out, int t, const Tw& tw) { inv_stage2(in, out, t, tw.w2i); }
 
 template <int P3>
 FB_HD void inv_stage3_p(const c2* in, c2* out, int q) {

@@ -30,6 +30,9 @@ size_t br_wide_table_bytes();
 void br_wide_make_table(c2* host_tab);
 cudaError_t launch_blind_rotate_wide(const c2* fbsk, const uint64_t* small, const uint64_t* luts, const uint32_t* lut_idx,
                                      uint64_t* out, const int32_t* out_rows, const c2* wtab, int count, int skew, int prefetch, cudaStream_t st);
+// latency variant for levels between one and two waves of SMs: two PBS per CTA of 512 threads, twiddles in tensor memory (br_wide2.cu)
+cudaError_t launch_blind_rotate_wide2(const c2* fbsk, const uint64_t* small, const uint64_t* luts, const uint32_t* lut_idx,
+                                      uint64_t* out, const int32_t* out_rows, const c2* wtab, int count, int skew, int prefetch, int sample_offset, cudaStream_t st);
 // cluster variant: one PBS per pair of CTAs (br_duo.cu)
 size_t br_duo_table_bytes();
 void br_duo_make_table(c2* host_tab);

@@ -75,11 +75,12 @@ def test_fourier_key_matches_emulation(server_key, gpu_key):
     assert np.abs(got - exp).max() < 1e-11 * scale
 
 
-BR_VARIANTS = {   # name -> (cluster threshold, latency threshold); None = leave the default
-    "cluster": (1 << 30, 0),         # one PBS per pair of SMs (br_duo.cu)
-    "latency": (0, 1 << 30),         # one PBS per CTA (br_wide.cu)
-    "throughput": (0, 0),            # up to 4 PBS per CTA (kernels.cu)
-    "default": (None, None),         # dispatch by batch size, short tails behind full throughput waves included
+BR_VARIANTS = {   # name -> (cluster threshold, latency threshold, wide_pair); None = leave the default
+    "cluster": (1 << 30, 0, None),       # one PBS per pair of SMs (br_duo.cu)
+    "latency": (0, 1 << 30, 0),          # one PBS per CTA (br_wide.cu)
+    "pair": (0, 1 << 30, 2),             # two PBS per CTA, twiddles in tensor memory (br_wide2.cu)
+    "throughput": (0, 0, None),          # up to 4 PBS per CTA (kernels.cu)
+    "default": (None, None, None),       # dispatch by batch size, short tails behind full throughput waves included
 }
 
 
@@ -88,9 +89,10 @@ class _Variant:
         self.key, self.name = key, name
 
     def __enter__(self):
-        c, l = BR_VARIANTS[self.name]
+        c, l, p = BR_VARIANTS[self.name]
         self.prev_c = self.key.set_cluster_threshold(c) if c is not None else None
         self.prev_l = self.key.set_latency_threshold(l) if l is not None else None
+        self.prev_p = self.key.set_option("wide_pair", p) if p is not None else None
         return self.name
 
     def __exit__(self, *exc):
@@ -98,6 +100,8 @@ class _Variant:
             self.key.set_cluster_threshold(self.prev_c)
         if self.prev_l is not None:
             self.key.set_latency_threshold(self.prev_l)
+        if self.prev_p is not None:
+            self.key.set_option("wide_pair", self.prev_p)
 
 
 @pytest.fixture(params=list(BR_VARIANTS))
@@ -160,7 +164,7 @@ def test_bootstrap_stagewise_against_oracle(client_key, server_key, gpu_key, br_
 def test_bootstrap_batch_size_boundaries(count, fck, gpu_key, br_variant):
     # the throughput blind rotation picks 1..4 samples per SM from the batch size (ragged last CTAs at every
     # boundary); the latency one runs in waves of one CTA per PBS
-    if br_variant in ("latency", "cluster") and count > 445:
+    if br_variant in ("latency", "pair", "cluster") and count > 445:
         pytest.skip("the narrow-level variants are never chosen for wide batches")
     msgs = (np.arange(count) * 7 + 3) % 16
     base = fck.encrypt_blocks(msgs[:min(count, 96)], seed=77)
@@ -184,9 +188,11 @@ def test_blind_rotation_variants_agree(client_key, gpu_key):
     luts = np.stack([tfhe.make_lut(f) for f in fs])
     idx = (np.arange(n) % 2).astype(np.uint32)
     outs = {}
-    for name in ("cluster", "latency", "throughput"):
+    for name in ("cluster", "latency", "pair", "throughput"):
         with _Variant(gpu_key, name):
             outs[name] = gpu_key.pbs(cts, luts, idx)
+    # the pair kernel runs the stages of the latency kernel with the same twiddles: not one bit differs
+    assert (outs["pair"] == outs["latency"]).all()
     exp_msg = np.array([fs[i](int(m)) & 15 for m, i in zip(msgs, idx)], dtype=np.uint64)
     for name, got in outs.items():
         ph = tfhe.phase_batch(client_key.big, got)
@@ -197,7 +203,7 @@ def test_blind_rotation_variants_agree(client_key, gpu_key):
     # the mask words are not comparable (a last-bit difference of an f64 rounding changes later digits, i.e. the
     # noise realisation), the phases are: both are encryptions of the same value with noise of the same size
     ph_t = tfhe.phase_batch(client_key.big, outs["throughput"])
-    for name in ("cluster", "latency"):
+    for name in ("cluster", "latency", "pair"):
         assert np.abs(tfhe.torus_err(tfhe.phase_batch(client_key.big, outs[name]), ph_t)).max() < 2 * PBS_ERR_MAX, name
 
 

@@ -1,0 +1,16 @@
+#!/bin/bash
+# Round-2 evidence for the throughput path: raw-PBS batch sweep, launch list of the bench command, full capture of the
+# fused blind rotation and of the tcgen05 keyswitch GEMM, DRAM traffic of both at the bench batch size.
+#   gpurun --timeout 1500 -- bash tools/gpu_r02_final.sh r02
+TAG=${1:-r02}
+OUT=gpurun_out
+mkdir -p $OUT
+timeout 300 python tools/batch_sweep.py $OUT/batch_sweep_$TAG.json > $OUT/batch_sweep_$TAG.log 2>&1; echo "sweep exit $?"; cat $OUT/batch_sweep_$TAG.log | cut -c1-250
+SMALL="python bench.py --steps 2 --warmup 3 --batch 592 --no-cpu-baseline --no-match"
+timeout 300 $SMALL > $OUT/plain_$TAG.log 2>&1 &&
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $OUT/launches_$TAG.csv $SMALL > $OUT/ncu_list_$TAG.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:blind_rotate_fused -s 3 -c 1 -o $OUT/prof_br_$TAG -f $SMALL > $OUT/ncu_br_$TAG.log 2>&1
+BIG="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-match"
+timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:"blind_rotate|ks_umma|ks_decompose" -s 9 -c 3 --csv --log-file $OUT/traffic_$TAG.csv $BIG > $OUT/ncu_traffic_$TAG.log 2>&1
+tail -4 $OUT/traffic_$TAG.csv | cut -c1-400
+ls -la $OUT | tail -8
