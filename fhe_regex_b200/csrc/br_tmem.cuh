@@ -80,6 +80,21 @@ __device__ __forceinline__ void tmem_ld32_wait(uint32_t (&v)[32]) {
                :
                : "memory");
 }
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_wait(uint32_t (&v)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                 "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+               :
+               : "memory");
+}
 // shared memory -> tensor memory, asynchronous: 64 rows of 16 bytes (row r at saddr + 16 r) into 4 columns at tcol of lanes
 // 0-31 and 64-95 (rows 0-31) and lanes 32-63 and 96-127 (rows 32-63).  Semantics probed on B200:
 // profiles/r02_tmem_cp_probe.txt.  Issued by one thread; completion through tmem_commit on an mbarrier.
