@@ -53,6 +53,7 @@ extern "C" int fb_ctx_create(fb_ctx** out, int device) {
   ctx->device = device;
   ctx->quantum = prop.multiProcessorCount * fb::br_samples_per_cta();
   ctx->sms = prop.multiProcessorCount;
+  ctx->dist_shard_min = ctx->sms;
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete ctx;
     g_create_err = "cudaSetDevice / cudaStreamCreate failed";
@@ -352,6 +353,7 @@ const OptionDesc kOptions[] = {
     {"wide_pair", 0, 2},                    // latency kernel with two PBS per CTA: 0 never, 1 for batches between one and two waves of SMs, 2 for every narrow batch
     {"wide_pair_prefetch", 0, 2},           // pair kernel: GGSW groups fetched before the pre-MAC barrier
     {"wide_pair_offset", 0, 100000},        // pair kernel: cycles the second sample of a CTA starts late
+    {"dist_shard_min", 0, 1 << 30},         // fb_has_match_dist: levels of at most this many PBS are computed by every rank instead of being sharded (default: the SM count)
 };
 int64_t* option_slot(fb_ctx* ctx, const char* name, int64_t& shadow, int& which) {
   for (int i = 0; i < (int)(sizeof(kOptions) / sizeof(kOptions[0])); i++)
@@ -370,6 +372,7 @@ int64_t* option_slot(fb_ctx* ctx, const char* name, int64_t& shadow, int& which)
         case 9: shadow = ctx->wide_pair; break;
         case 10: shadow = ctx->wide_pair_prefetch; break;
         case 11: shadow = ctx->wide_pair_offset; break;
+        case 12: shadow = ctx->dist_shard_min; break;
       }
       return &shadow;
     }
@@ -405,6 +408,7 @@ extern "C" int fb_set_option(fb_ctx* ctx, const char* name, int64_t value) {
     case 9: ctx->wide_pair = (int)value; break;
     case 10: ctx->wide_pair_prefetch = (int)value; break;
     case 11: ctx->wide_pair_offset = (int)value; break;
+    case 12: ctx->dist_shard_min = (int)value; break;
   }
   return FB_OK;
 }

@@ -59,6 +59,7 @@ struct fb_ctx {
   // multi-GPU: this context as a rank of an NCCL communicator (comm.cu); ncclComm_t kept opaque here
   void* comm = nullptr;
   int comm_rank = 0, comm_world = 1;
+  int dist_shard_min = 148;    // fb_has_match_dist: levels of at most this many PBS (one wave of SMs) are computed by every rank, not sharded (option "dist_shard_min")
   uint64_t comm_exchanges = 0, comm_bytes = 0;   // level exchanges issued / ciphertext bytes gathered per rank
   // scratch for the batch entry points
   fb_devbuf in, small, out, luts, lut_idx, digits;

@@ -352,11 +352,11 @@ cudaError_t launch_blind_rotate(const c2* fbsk, const uint64_t* small, const uin
   if (count <= 0) return cudaSuccess;
   // Throughput wants 4 samples per SM; a batch that does not fill the GPU at that width (the narrow DAG
   // levels of a regex match) finishes sooner with fewer samples contending for each SM.
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-  }
+  static int sms_of[64] = {};   // per device: a process may hold contexts on several GPUs
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+  int& sms = sms_of[dev & 63];
+  if (sms == 0 && (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)) sms = 148;
   // measured (tools/wave_times.py): one sample per SM on all 148 SMs takes 6.6 ms, two per SM on 74-148 SMs 5.9 ms,
   // one per SM on <= 74 SMs 4.9-5.7 ms -- a lone sample per SM is only worth it while half the SMs stay idle
   if (2 * count <= sms) return launch_br_s<1>(fbsk, small, luts, lut_idx, out, out_rows, tabs, count, st);

@@ -154,9 +154,18 @@ int run_plan(fb_ctx* ctx, const Plan& plan, const uint64_t* h_in, size_t n_in_ro
         if (rc) { cleanup(); return rc; }
       }
       if (o.n_pbs > 0) {
+        uint64_t* d_level_out = d_arena + (size_t)o.out_base * FB_LWE_BIG_WORDS;
+        // a level that one GPU bootstraps in a single wave of SMs gains nothing from being cut up: every rank computes all of
+        // it (the kernels are deterministic, the arenas stay identical) and the exchange is skipped
+        if (o.n_pbs <= ctx->dist_shard_min) {
+          rc = fb_run_keyswitch(ctx, d_arena, d_i32 + o.in_rows, d_small, o.n_pbs);
+          if (rc) { cleanup(); return rc; }
+          rc = fb_run_blind_rotate(ctx, d_small, d_luts, d_u32 + o.lut_idx, d_level_out, nullptr, o.n_pbs);
+          if (rc) { cleanup(); return rc; }
+          continue;
+        }
         size_t lo, hi;
         fb_comm_slice((size_t)o.n_pbs, ctx->comm_rank, ctx->comm_world, &lo, &hi);
-        uint64_t* d_level_out = d_arena + (size_t)o.out_base * FB_LWE_BIG_WORDS;
         if (hi > lo) {
           rc = fb_run_keyswitch(ctx, d_arena, d_i32 + o.in_rows + lo, d_small, (int)(hi - lo));
           if (rc) { cleanup(); return rc; }

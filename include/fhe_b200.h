@@ -67,7 +67,14 @@ int fb_sync(fb_ctx* ctx);
  *   "cluster_threshold"      batches up to this many PBS run the one-PBS-per-SM-pair blind rotation (default 0 = never)
  *   "br_variant"             throughput blind rotation at 4 PBS per SM: 0 phase-by-phase body, 1 fused body, 2 fused body with
  *                            the digits through the integer-to-double unit (default 2)
+ *   "br_stagger"             fused throughput kernel: start skew between the samples of a CTA, cycles per sample index (default 0)
+ *   "ks_variant"             keyswitch GEMM: 0 mma.sync, 1 tcgen05.mma kind::i8 with TMA operands and TMEM accumulators (default 1)
  *   "wide_skew", "wide_prefetch"   tuning of the latency kernel (defaults 200 cycles, 3 groups)
+ *   "wide_pair"              two PBS per CTA (twiddles in tensor memory): 1 for batches between one and two waves of SMs
+ *                            (149 .. 296 on a B200, default), 2 for every narrow batch, 0 never
+ *   "wide_pair_prefetch", "wide_pair_offset"   tuning of the two-PBS-per-CTA kernel (defaults 1 group, 0 cycles)
+ *   "dist_shard_min"         fb_has_match_dist: levels of at most this many PBS are bootstrapped by every rank instead of being
+ *                            cut into slices and exchanged (default: the SM count, i.e. what one GPU does in one wave)
  *   "plan_reference_shaped"  1: has_match evaluates every variant the reference enumerates (default 0: implied OR
  *                            operands are absorbed; same decrypted result)
  *   "plan_timing"            1: planner phase times on stderr

@@ -159,9 +159,10 @@ pub fn has_match_flat(sk: &B200ServerKey, content: &[u64], n_chars: usize, patte
     Ok((out, stats))
 }
 
-/// One rank's share of a match sharded over `world` GPUs without NCCL: the rank-th contiguous slice of the final OR's operands
-/// after global absorption (reference-shaped plan: the variants of start offsets i % world == rank).  Gather the first 2049
-/// words of every rank's result and finish with `or_fold`.
+/// One rank's share of a match sharded over `world` GPUs without NCCL: the rank-th contiguous slice (operands sorted by
+/// content position, `[n r / world, n (r + 1) / world)`) of the final OR's operands, after global absorption in the default plan
+/// and of every enumerated variant in the reference-shaped one.  Gather the first 2049 words of every rank's result and
+/// finish with `or_fold`.
 pub fn has_match_shard_flat(sk: &B200ServerKey, content: &[u64], n_chars: usize, pattern: &str, rank: i32, world: i32) -> Result<Vec<u64>> {
     let mut out = vec![0u64; FB_RADIX_BLOCKS * FB_LWE_BIG_WORDS];
     let pat = CString::new(pattern)?;

@@ -64,7 +64,7 @@ def test_sharded_match_world2_gloo(tmp_path):
 DIST_CASES = CASES + [("xabbcxabbbbcxx", "/ab{2,4}c/"), ("x" * 40 + "aabc" + "x" * 20, "/a+b?c/"), ("abab", "/^(ab|c)+$/"), ("", "/^$/")]
 
 
-def _dist_level_worker(rank, world, port, out_path):
+def _dist_level_worker(rank, world, port, out_path, shard_min=0):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -97,6 +97,8 @@ def _dist_level_worker(rank, world, port, out_path):
                     arena[int(row)] = v
                 n = len(lv["in_rows"])
                 lo, hi = n * rank // world, n * (rank + 1) // world
+                if n <= shard_min:                    # narrow level: every rank computes all of it, no exchange (option dist_shard_min)
+                    lo, hi = 0, n
                 base = lv["out_row_base"]
                 outs = []
                 for b in range(lo, hi):
@@ -104,9 +106,10 @@ def _dist_level_worker(rank, world, port, out_path):
                     assert 0 <= x <= 15, "PBS input outside the message space"
                     outs.append(int(lut_f[int(lv["lut_idx"][b]), x]))
                 arena[base + lo: base + hi] = torch.tensor(outs, dtype=torch.int64)
-                arena[base: base + lo] = -99          # rows this rank did not compute: must come from the exchange
-                arena[base + hi: base + n] = -99
-                _exchange(arena, base, n, rank, world)
+                if n > shard_min:
+                    arena[base: base + lo] = -99      # rows this rank did not compute: must come from the exchange
+                    arena[base + hi: base + n] = -99
+                    _exchange(arena, base, n, rank, world)
             results.append((int(arena[plan["result_row"]]), rp.has_match(content, pattern)))
     # every rank ends with the same result
     mine = torch.tensor([r[0] for r in results], dtype=torch.int64)
@@ -130,10 +133,10 @@ def _exchange(arena, base, n, rank, world):
             arena[base + lo: base + hi] = buf
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_level_sharded_match_gloo(tmp_path, world):
+@pytest.mark.parametrize("world,shard_min", [(2, 0), (3, 0), (2, 6)])
+def test_level_sharded_match_gloo(tmp_path, world, shard_min):
     out = str(tmp_path / "res.txt")
-    mp.spawn(_dist_level_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    mp.spawn(_dist_level_worker, args=(world, _free_port(), out, shard_min), nprocs=world, join=True)
     results, same = eval(open(out).read())
     assert same
     assert len(results) == 2 * len(DIST_CASES)
