@@ -41,9 +41,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 FLOP_PER_PBS = 742 * 262144            # 4 transforms x (5*1024*10 + 6*1024) + 4*1024*8 per CMUX
-# DRAM bytes of one blind_rotate launch at the default batch, from the ncu pass recorded in
-# profiles/r01_traffic_bench_batch.csv (dram__bytes_read.sum + dram__bytes_write.sum, B = 28 416)
-BR_TRAFFIC_MEASURED = {28416: 286415360 + 455150336}
+# DRAM bytes of one blind_rotate_fused launch at the default batch, from the ncu pass recorded in
+# profiles/r02_traffic_bench_batch.csv (dram__bytes_read.sum + dram__bytes_write.sum, B = 28 416)
+BR_TRAFFIC_MEASURED = {28416: 394445568 + 570365696}
 BSK_BYTES = 742 * 4 * 1024 * 16
 KS_MAC_PER_PBS = 2048 * 5 * 743
 KS_BYTES_PER_LAUNCH_KEY = 2048 * 5 * 743 * 8
@@ -337,9 +337,9 @@ def main():
                        "batch_per_gpu": B, "global_batch": B * world, "luts": int(luts_np.shape[0]),
                        "l2": "inputs+outputs %.0f MB per step > 126 MB L2; keys (109 MB) are re-read by design" % (2 * B * BIG * 8 / 1e6),
                        "parallelism": "replicated keys, batch sharded x%d" % world},
-            "roofline": {"kernel": "blind_rotate_kernel", "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+            "roofline": {"kernel": "blind_rotate_fused_kernel<4, 1> (br_fused.cu)", "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak if fp64_peak else None, "traffic": BR_TRAFFIC_MEASURED.get(B),
-                         "traffic_unit": "B/launch (ncu dram read+write, profiles/r01_traffic_bench_batch.csv)",
+                         "traffic_unit": "B/launch (ncu dram read+write, profiles/r02_traffic_bench_batch.csv)",
                          "algorithmic_bytes": BSK_BYTES + B * (SMALL + BIG) * 8 + int(luts_np.nbytes),
                          "peak_source": "measured live: fb_measure_fp64_peak (DFMA chains); nominal 148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2",
                          "flop_per_pbs": FLOP_PER_PBS, "avg_launch_ms": br_ms, "share_of_step": kst["br_ms"] / (kst["br_ms"] + kst["ks_ms"] + kst["lin_ms"]),
