@@ -117,10 +117,12 @@ FB_HD uint32_t double_lo32(double d) {
 }
 
 // balanced base-2^23 digit of a 32-bit torus difference, round(diff / 2^9) in [-2^22, 2^22], as a double.
-// int -> double without the conversion unit: the double 2^52 + 2^31 + q carries q + 2^31 in its low word.
+// int -> double without the conversion unit and without the shift: d = diff + 2^8 + 2^31 (the rounding offset and a flip of the
+// sign bit in one add) with its low 9 bits cleared is 512 (q + 2^22), q = floor((diff + 2^8) / 2^9); as the low mantissa word of
+// a double with exponent 2^43 (ulp 2^-9) it reads 2^43 + 2^22 + q.  One add, one AND and one DADD per digit.
 FB_HD double pbs_digit32(uint32_t diff) {
-  const int32_t q = (int32_t)(diff + 256u) >> 9;
-  return hilo_to_double(0x43300000u, (uint32_t)q ^ 0x80000000u) - 4503601774854144.0;  // 2^52 + 2^31
+  const uint32_t lo = (diff + 0x80000100u) & 0xFFFFFE00u;
+  return hilo_to_double(0x42A00000u, lo) - 8796097216512.0;  // 2^43 + 2^22
 }
 
 // decompose (acc*X^a - acc) of polynomial accp into the folded FFT input (digits; the twist is in fft32_fwd_twist)
@@ -180,9 +182,15 @@ FB_HD size_t fbsk_index(int i, int pin, int jout, int k) {
   return (((size_t)i * 2 + pin) * 2 + jout) * kHalfN + k;
 }
 
-// ---- split transposes: the real and the imaginary planes go through one [2][1024] double buffer one
+// ---- split transposes: the real and the imaginary planes go through one [2][kPlaneDoubles] double buffer one
 // after the other (half the shared memory of a complex buffer; 4 two-warp barriers per transpose).
-// Element (row k1, column c) of polynomial p lives at p*1024 + k1*32 + (c ^ k1).
+// Element (row k1, column c) of polynomial p lives at p*kPlaneDoubles + k1*34 + c: rows padded to 34 doubles instead of an
+// XOR swizzle.  Every access is then [one base register + immediate] (the swizzle cost a LOP3 + LEA per access, ~250
+// instructions per CMUX step, in a loop whose instruction supply is the scarce resource), a row is 16-byte aligned so the
+// row side moves two columns per 128-bit access, and both sides stay conflict-free: a column access touches 32 consecutive
+// doubles; in a row access a quarter-warp holds 8 consecutive rows, 8 x 272 bytes apart = 8 different 16-byte bank groups.
+constexpr int kPlaneRow = 34;
+constexpr int kPlaneDoubles = 32 * kPlaneRow;   // 1088 per polynomial
 
 // forward inter-pass twiddle in place: register q (row k1 = brev5(q)) *= exp(i*pi*lane*(1-4*k1)/2048)
 FB_HD void fwd_twiddle_inplace(double (&xr)[32], double (&xi)[32], const c2* tab_f, int lane) {
@@ -211,13 +219,18 @@ FB_HD void col_store_brev(const double (&x)[32], double* plane_p, int lane) {
 #pragma unroll
   for (int q = 0; q < 32; q++) {
     const int k1 = brev5(q);
-    plane_p[k1 * 32 + (lane ^ k1)] = x[q];
+    plane_p[k1 * kPlaneRow + lane] = x[q];
   }
 }
 // row reader (thread = row k1 of polynomial pp, register c = column c)
 FB_HD void row_load(double (&x)[32], const double* plane_pp, int k1) {
+  const c2* row = reinterpret_cast<const c2*>(plane_pp + k1 * kPlaneRow);
 #pragma unroll
-  for (int c = 0; c < 32; c++) x[c] = plane_pp[k1 * 32 + (c ^ k1)];
+  for (int h = 0; h < 16; h++) {
+    const c2 v = row[h];
+    x[2 * h] = v.x;
+    x[2 * h + 1] = v.y;
+  }
 }
 // inverse inter-pass twiddle in place: register c *= exp(-i*pi*c*(1-4*k1)/2048)
 FB_HD void inv_twiddle_inplace(double (&xr)[32], double (&xi)[32], const c2* tab_i, int k1) {
@@ -243,15 +256,21 @@ FB_HD void inv_twiddle_inplace(double (&xr)[32], double (&xi)[32], const c2* tab
 }
 // row writer (thread = row k1, register c = column c)
 FB_HD void row_store(const double (&x)[32], double* plane_pp, int k1) {
+  c2* row = reinterpret_cast<c2*>(plane_pp + k1 * kPlaneRow);
 #pragma unroll
-  for (int c = 0; c < 32; c++) plane_pp[k1 * 32 + (c ^ k1)] = x[c];
+  for (int h = 0; h < 16; h++) {
+    c2 v;
+    v.x = x[2 * h];
+    v.y = x[2 * h + 1];
+    row[h] = v;
+  }
 }
 // column reader into the bit-reversed register order fft32_dit_inv wants (register q = row brev5(q))
 FB_HD void col_load_brev(double (&x)[32], const double* plane_p, int lane) {
 #pragma unroll
   for (int q = 0; q < 32; q++) {
     const int k1 = brev5(q);
-    x[q] = plane_p[k1 * 32 + (lane ^ k1)];
+    x[q] = plane_p[k1 * kPlaneRow + lane];
   }
 }
 
@@ -309,20 +328,37 @@ FB_HD void phaseA_f1(double (&xr)[32], double (&xi)[32], const unsigned char* sm
   phaseA_f1_seq<CVT>(xr, xi, sm, shp_off, t0, own, fb_make_iseq<32>{});
 }
 
-// round(frac(k * ts) * 2^32) mod 2^32 in three FMAs, the pending factor k of the untwist folded in:
-// s1 = M + rint(k*ts); g = M - rint(k*ts)*2^32 (exact); s2 = (k*ts - rint(k*ts))*2^32 + M; |k*ts| < 2^51
-FB_HD uint32_t torus32_round_scaled(double ts, double k) {
-  const double kM = 6755399441055744.0;                                  // 1.5 * 2^52
-  const double kC = 6755399441055744.0 * 4294967296.0 + 6755399441055744.0;  // M * 2^32 + M (exact: 34 significant bits)
-  const double s1 = fb_fma(ts, k, kM);
-  const double g = fb_fma(s1, -4294967296.0, kC);
-  return double_lo32(fb_fma(ts, k * 4294967296.0, g));
+// round(frac(k * ts) * 2^32) mod 2^32 in three FP64 instructions, the pending factor k of the untwist folded in.  Everything is
+// done at the scale 2^32 so that ONE per-slot constant (k32 = k * 2^32) is needed:
+//   s1 = ts * k32 + 1.5 * 2^84        the sum rounds to a multiple of 2^32: s1 = 1.5 * 2^84 + 2^32 rint(k ts)
+//   g  = (1.5 * 2^84 + 1.5 * 2^52) - s1 = 1.5 * 2^52 - 2^32 rint(k ts)          (exact)
+//   r  = ts * k32 + g = 2^32 (k ts - rint(k ts)) + 1.5 * 2^52                  (low word: the torus value); |k ts| < 2^51
+FB_HD uint32_t torus32_round_scaled32(double ts, double k32) {
+  const double kMp = 29014219670751100192948224.0;                         // 1.5 * 2^84
+  const double kC = 29014219670751100192948224.0 + 6755399441055744.0;     // + 1.5 * 2^52 (exact: 34 significant bits)
+  const double s1 = fb_fma(ts, k32, kMp);
+  const double g = kC - s1;
+  return double_lo32(fb_fma(ts, k32, g));
 }
-// torus increments of slot R after fft32_i2_fin (pending untwist magnitudes and the 1/1024 of the transform)
+FB_HD uint32_t torus32_round_scaled(double ts, double k) { return torus32_round_scaled32(ts, k * 4294967296.0); }
+// torus increments of slot R after fft32_i2_fin (pending untwist magnitudes and the 1/1024 of the transform); the 64 scale factors
+// come from a constant-bank table (as literals each costs two 32-bit moves per CMUX step)
+#define FB_PC1(R) fb_i2_kre(R) * (4294967296.0 / 1024.0), fb_i2_kim(R) * (4294967296.0 / 1024.0)
+#define FB_PC4(R) FB_PC1(R), FB_PC1(R + 1), FB_PC1(R + 2), FB_PC1(R + 3)
+#define FB_PCTAB_INIT { FB_PC4(0), FB_PC4(4), FB_PC4(8), FB_PC4(12), FB_PC4(16), FB_PC4(20), FB_PC4(24), FB_PC4(28) }
+#if defined(__CUDACC__)
+static __constant__ double fb_pctab_d[64] = FB_PCTAB_INIT;
+#endif
+static const double fb_pctab_h[64] = FB_PCTAB_INIT;
+#if defined(__CUDA_ARCH__)
+#define FBPC(i) fb_pctab_d[i]
+#else
+#define FBPC(i) fb_pctab_h[i]
+#endif
 template <int R>
 FB_HD void phaseC_slot(const double (&xr)[32], const double (&xi)[32], uint32_t& inc0, uint32_t& inc1) {
-  inc0 = torus32_round_scaled(xr[R], fb_i2_kre(R) * (1.0 / 1024.0));
-  inc1 = torus32_round_scaled(xi[R], fb_i2_kim(R) * (1.0 / 1024.0));
+  inc0 = torus32_round_scaled32(xr[R], FBPC(2 * R));
+  inc1 = torus32_round_scaled32(xi[R], FBPC(2 * R + 1));
 }
 
 // Host-side: twiddle tables.  tab_f[e][lane], tab_i[e][k1], e < 4: "lo" l = e; e >= 4: "hi" h = e-4.

@@ -141,8 +141,8 @@ blind_rotate_fused_kernel(const c2* __restrict__ fbsk, const uint64_t* __restric
   extern __shared__ __align__(128) unsigned char smem[];
   c2* stage = reinterpret_cast<c2*>(smem);                                             // [2][2][1024]
   uint32_t* shadow_all = reinterpret_cast<uint32_t*>(smem + kGgswBytes);                // [S][2][2048], every polynomial at a multiple of 8 KiB
-  double* plane_all = reinterpret_cast<double*>(smem + kGgswBytes + (size_t)S * 16384);  // [S][2][1024]
-  c2* tab_f = reinterpret_cast<c2*>(smem + kGgswBytes + (size_t)S * 32768);              // [12][32]
+  double* plane_all = reinterpret_cast<double*>(smem + kGgswBytes + (size_t)S * 16384);  // [S][2][kPlaneDoubles]
+  c2* tab_f = reinterpret_cast<c2*>(smem + kGgswBytes + (size_t)S * (16384 + 2 * kPlaneDoubles * sizeof(double)));   // [12][32]
   c2* tab_i = tab_f + kTabEntries * 32;                                                 // [12][32]
   uint16_t* at_all = reinterpret_cast<uint16_t*>(tab_i + kTabEntries * 32);             // [S][768]
   uint8_t* need = reinterpret_cast<uint8_t*>(at_all + S * 768);                         // [768]
@@ -257,7 +257,7 @@ blind_rotate_fused_kernel(const c2* __restrict__ fbsk, const uint64_t* __restric
   if (active) {
     const uint32_t shp_off = (uint32_t)kGgswBytes + (uint32_t)(s * 2 + w) * 8192u;   // byte offset of this polynomial's accumulator copy
     uint32_t* shp = shadow_all + (size_t)s * 2 * kN + (size_t)w * kN;
-    double* plane = plane_all + (size_t)s * 2 * kHalfN;
+    double* plane = plane_all + (size_t)s * 2 * kPlaneDoubles;
     const int bar_id = 1 + s;
     const uint32_t tacc = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 64);
 
@@ -313,13 +313,13 @@ blind_rotate_fused_kernel(const c2* __restrict__ fbsk, const uint64_t* __restric
       // phase A + forward pass 1, interleaved
       phaseA_f1<(V & 1) != 0>(xr, xi, smem, shp_off, a & 4095u, lane);
       fwd_twiddle_inplace(xr, xi, tab_f, lane);
-      col_store_brev(xr, plane + w * kHalfN, lane);
+      col_store_brev(xr, plane + w * kPlaneDoubles, lane);
       bar_sync(bar_id, 64);
-      row_load(xr, plane + pp * kHalfN, k1);
+      row_load(xr, plane + pp * kPlaneDoubles, k1);
       bar_sync(bar_id, 64);
-      col_store_brev(xi, plane + w * kHalfN, lane);
+      col_store_brev(xi, plane + w * kPlaneDoubles, lane);
       bar_sync(bar_id, 64);
-      row_load(xi, plane + pp * kHalfN, k1);
+      row_load(xi, plane + pp * kPlaneDoubles, k1);
       bar_sync(bar_id, 64);
       // forward pass 2, Fourier MAC, inverse pass 1: block by block
       fft32_fwd_s12(xr, xi);
@@ -346,14 +346,14 @@ blind_rotate_fused_kernel(const c2* __restrict__ fbsk, const uint64_t* __restric
       }
       fft32_inv_s45(xr, xi);
       inv_twiddle_inplace(xr, xi, tab_i, k1);
-      row_store(xr, plane + pp * kHalfN, k1);
+      row_store(xr, plane + pp * kPlaneDoubles, k1);
       bar_sync(bar_id, 64);
 
-      col_load_brev(xr, plane + w * kHalfN, lane);
+      col_load_brev(xr, plane + w * kPlaneDoubles, lane);
       bar_sync(bar_id, 64);
-      row_store(xi, plane + pp * kHalfN, k1);
+      row_store(xi, plane + pp * kPlaneDoubles, k1);
       bar_sync(bar_id, 64);
-      col_load_brev(xi, plane + w * kHalfN, lane);
+      col_load_brev(xi, plane + w * kPlaneDoubles, lane);
       bar_sync(bar_id, 64);
       // inverse pass 2 + phase C, interleaved
       fft32_i2_head(xr, xi);

@@ -22,8 +22,8 @@ namespace fb {
 __global__ void __launch_bounds__(64, 1)
 bsk_convert_kernel(const uint64_t* __restrict__ bsk_std, c2* __restrict__ fbsk, const c2* __restrict__ tabs_g) {
   extern __shared__ __align__(128) unsigned char smem[];
-  double* plane = reinterpret_cast<double*>(smem);            // [2][1024]
-  c2* tab_f = reinterpret_cast<c2*>(plane + 2 * kHalfN);       // [12][32]
+  double* plane = reinterpret_cast<double*>(smem);            // [2][kPlaneDoubles]
+  c2* tab_f = reinterpret_cast<c2*>(plane + 2 * kPlaneDoubles);   // [12][32]
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
   for (int t = tid; t < kTabEntries * 32; t += 64) tab_f[t] = tabs_g[t];
   __syncthreads();
@@ -33,13 +33,13 @@ bsk_convert_kernel(const uint64_t* __restrict__ bsk_std, c2* __restrict__ fbsk, 
   fft32_fwd_twist(xr, xi);
   fwd_twiddle_inplace(xr, xi, tab_f, lane);
   const int pp = lane >> 4, k1 = 16 * w + (lane & 15);
-  col_store_brev(xr, plane + w * kHalfN, lane);
+  col_store_brev(xr, plane + w * kPlaneDoubles, lane);
   __syncthreads();
-  row_load(xr, plane + pp * kHalfN, k1);
+  row_load(xr, plane + pp * kPlaneDoubles, k1);
   __syncthreads();
-  col_store_brev(xi, plane + w * kHalfN, lane);
+  col_store_brev(xi, plane + w * kPlaneDoubles, lane);
   __syncthreads();
-  row_load(xi, plane + pp * kHalfN, k1);
+  row_load(xi, plane + pp * kPlaneDoubles, k1);
   fft32_fwd(xr, xi);
   c2* dst = fbsk + (row * 2 + pp) * kHalfN + k1;
 #pragma unroll
@@ -77,8 +77,8 @@ blind_rotate_kernel(const c2* __restrict__ fbsk, const uint64_t* __restrict__ sm
   extern __shared__ __align__(128) unsigned char smem[];
   c2* stage = reinterpret_cast<c2*>(smem);                                             // [2][2][1024]
   uint32_t* shadow_all = reinterpret_cast<uint32_t*>(smem + kGgswBytes);                // [S][2][2048]
-  double* plane_all = reinterpret_cast<double*>(smem + kGgswBytes + (size_t)S * 16384);  // [S][2][1024]
-  c2* tab_f = reinterpret_cast<c2*>(smem + kGgswBytes + (size_t)S * 32768);              // [12][32]
+  double* plane_all = reinterpret_cast<double*>(smem + kGgswBytes + (size_t)S * 16384);  // [S][2][kPlaneDoubles]
+  c2* tab_f = reinterpret_cast<c2*>(smem + kGgswBytes + (size_t)S * (16384 + 2 * kPlaneDoubles * sizeof(double)));   // [12][32]
   c2* tab_i = tab_f + kTabEntries * 32;                                                 // [12][32]
   uint16_t* at_all = reinterpret_cast<uint16_t*>(tab_i + kTabEntries * 32);             // [S][768]
   uint8_t* need = reinterpret_cast<uint8_t*>(at_all + S * 768);                         // [768]
@@ -153,7 +153,7 @@ blind_rotate_kernel(const c2* __restrict__ fbsk, const uint64_t* __restrict__ sm
 
   if (active) {
     uint32_t* shp = shadow_all + (size_t)s * 2 * kN + (size_t)w * kN;  // shared copy of polynomial w of this sample
-    double* plane = plane_all + (size_t)s * 2 * kHalfN;
+    double* plane = plane_all + (size_t)s * 2 * kPlaneDoubles;
     const int bar_id = 1 + s;
     // this warp's 64 TMEM columns: coefficient 32r+lane in column 2r, 32r+lane+1024 in column 2r+1
     const uint32_t tacc = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 64);
@@ -200,13 +200,13 @@ blind_rotate_kernel(const c2* __restrict__ fbsk, const uint64_t* __restrict__ sm
       phaseA_load32(xr, xi, shp, a & 4095u, lane);
       fft32_fwd_twist(xr, xi);
       fwd_twiddle_inplace(xr, xi, tab_f, lane);
-      col_store_brev(xr, plane + w * kHalfN, lane);   // the plane is free: see the barrier after the last loads
+      col_store_brev(xr, plane + w * kPlaneDoubles, lane);   // the plane is free: see the barrier after the last loads
       bar_sync(bar_id, 64);
-      row_load(xr, plane + pp * kHalfN, k1);
+      row_load(xr, plane + pp * kPlaneDoubles, k1);
       bar_sync(bar_id, 64);
-      col_store_brev(xi, plane + w * kHalfN, lane);
+      col_store_brev(xi, plane + w * kPlaneDoubles, lane);
       bar_sync(bar_id, 64);
-      row_load(xi, plane + pp * kHalfN, k1);
+      row_load(xi, plane + pp * kPlaneDoubles, k1);
       bar_sync(bar_id, 64);                           // both warps have read: the next transpose may store at once
       // phase B: pass 2 -> Fourier MAC with the staged GGSW_i -> inverse pass 1 -> twiddle -> transpose
       fft32_fwd(xr, xi);
@@ -221,13 +221,13 @@ blind_rotate_kernel(const c2* __restrict__ fbsk, const uint64_t* __restrict__ sm
       release_stage(i);                           // this warp no longer reads the stage
       fft32_inv(xr, xi);
       inv_twiddle_inplace(xr, xi, tab_i, k1);
-      row_store(xr, plane + pp * kHalfN, k1);
+      row_store(xr, plane + pp * kPlaneDoubles, k1);
       bar_sync(bar_id, 64);
-      col_load_brev(xr, plane + w * kHalfN, lane);
+      col_load_brev(xr, plane + w * kPlaneDoubles, lane);
       bar_sync(bar_id, 64);
-      row_store(xi, plane + pp * kHalfN, k1);
+      row_store(xi, plane + pp * kPlaneDoubles, k1);
       bar_sync(bar_id, 64);
-      col_load_brev(xi, plane + w * kHalfN, lane);
+      col_load_brev(xi, plane + w * kPlaneDoubles, lane);
       bar_sync(bar_id, 64);
       // phase C: inverse pass 2 -> untwist, round to the 32-bit torus, accumulate (TMEM copy + shared copy)
       fft32_inv(xr, xi);
@@ -321,11 +321,11 @@ double fp64_peak_flops_per_launch(int ctas) { return (double)ctas * 256.0 * 8.0 
 int br_samples_per_cta() { return 4; }
 
 size_t br_smem_bytes(int S) {
-  return (size_t)kGgswBytes + (size_t)S * 32768 + 2 * kTabEntries * 32 * sizeof(c2) + (size_t)S * 768 * sizeof(uint16_t) + 768 + 16 + 32;
+  return (size_t)kGgswBytes + (size_t)S * (16384 + 2 * kPlaneDoubles * sizeof(double)) + 2 * kTabEntries * 32 * sizeof(c2) + (size_t)S * 768 * sizeof(uint16_t) + 768 + 16 + 32;
 }
 
 cudaError_t launch_bsk_convert(const uint64_t* bsk_std, c2* fbsk, const c2* tabs, cudaStream_t st) {
-  const size_t smem = 2 * kHalfN * sizeof(double) + kTabEntries * 32 * sizeof(c2);
+  const size_t smem = 2 * kPlaneDoubles * sizeof(double) + kTabEntries * 32 * sizeof(c2);
   cudaError_t e = cudaFuncSetAttribute(bsk_convert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   bsk_convert_kernel<<<kLweN * 2, 64, smem, st>>>(bsk_std, fbsk, tabs);

@@ -65,8 +65,8 @@ int fb_sync(fb_ctx* ctx);
 /* Every knob is per context and set explicitly; the library reads nothing from the environment.
  *   "latency_threshold"      batches up to this many PBS run the one-PBS-per-CTA blind rotation (default 296, 0 = never)
  *   "cluster_threshold"      batches up to this many PBS run the one-PBS-per-SM-pair blind rotation (default 0 = never)
- *   "br_variant"             throughput blind rotation at 4 PBS per SM: 0 phase-by-phase body, 1 fused body, 2 fused body with
- *                            the digits through the integer-to-double unit (default 2)
+ *   "br_variant"             throughput blind rotation at 4 PBS per SM: 0 phase-by-phase body, 1 fused body (default), 2 fused body
+ *                            with the digits through the integer-to-double unit, 3 / 4 = 1 / 2 with the Fourier key in tensor memory
  *   "br_stagger"             fused throughput kernel: start skew between the samples of a CTA, cycles per sample index (default 0)
  *   "ks_variant"             keyswitch GEMM: 0 mma.sync, 1 tcgen05.mma kind::i8 with TMA operands and TMEM accumulators (default 1)
  *   "wide_skew", "wide_prefetch"   tuning of the latency kernel (defaults 200 cycles, 3 groups)

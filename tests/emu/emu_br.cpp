@@ -15,9 +15,9 @@ struct Sample {
   std::vector<uint64_t> acc;   // [2][2048] (only used by the product check)
   std::vector<uint32_t> shadow; // [2][2048] 32-bit accumulator, shared copy (rotation reads of the decomposition)
   uint32_t master[2][32][64];  // [warp][lane][2r + half]: thread-private copy of the same words (tensor memory on the device)
-  std::vector<double> plane;   // [2][1024]: the re and the im planes pass through it one after the other
+  std::vector<double> plane;   // [2][kPlaneDoubles]: the re and the im planes pass through it one after the other
   Regs regs[2][32];            // [warp][lane]
-  Sample() : acc(2 * kN), shadow(2 * kN), plane(2 * kHalfN) {}
+  Sample() : acc(2 * kN), shadow(2 * kN), plane(2 * kPlaneDoubles) {}
 };
 
 static c2 g_tab_f[kTabEntries * 32], g_tab_i[kTabEntries * 32];
@@ -34,14 +34,14 @@ static void forward_passes(Sample& s) {
     }
   // barrier; re plane
   for (int w = 0; w < 2; w++)
-    for (int lane = 0; lane < 32; lane++) col_store_brev(s.regs[w][lane].xr, s.plane.data() + w * kHalfN, lane);
+    for (int lane = 0; lane < 32; lane++) col_store_brev(s.regs[w][lane].xr, s.plane.data() + w * kPlaneDoubles, lane);
   for (int w = 0; w < 2; w++)
-    for (int lane = 0; lane < 32; lane++) row_load(s.regs[w][lane].xr, s.plane.data() + (lane >> 4) * kHalfN, 16 * w + (lane & 15));
+    for (int lane = 0; lane < 32; lane++) row_load(s.regs[w][lane].xr, s.plane.data() + (lane >> 4) * kPlaneDoubles, 16 * w + (lane & 15));
   // barrier; im plane
   for (int w = 0; w < 2; w++)
-    for (int lane = 0; lane < 32; lane++) col_store_brev(s.regs[w][lane].xi, s.plane.data() + w * kHalfN, lane);
+    for (int lane = 0; lane < 32; lane++) col_store_brev(s.regs[w][lane].xi, s.plane.data() + w * kPlaneDoubles, lane);
   for (int w = 0; w < 2; w++)
-    for (int lane = 0; lane < 32; lane++) row_load(s.regs[w][lane].xi, s.plane.data() + (lane >> 4) * kHalfN, 16 * w + (lane & 15));
+    for (int lane = 0; lane < 32; lane++) row_load(s.regs[w][lane].xi, s.plane.data() + (lane >> 4) * kPlaneDoubles, 16 * w + (lane & 15));
   for (int w = 0; w < 2; w++)
     for (int lane = 0; lane < 32; lane++) fft32_fwd(s.regs[w][lane].xr, s.regs[w][lane].xi);
 }
@@ -55,13 +55,13 @@ static void inverse_passes(Sample& s) {
       inv_twiddle_inplace(R.xr, R.xi, g_tab_i, 16 * w + (lane & 15));
     }
   for (int w = 0; w < 2; w++)
-    for (int lane = 0; lane < 32; lane++) row_store(s.regs[w][lane].xr, s.plane.data() + (lane >> 4) * kHalfN, 16 * w + (lane & 15));
+    for (int lane = 0; lane < 32; lane++) row_store(s.regs[w][lane].xr, s.plane.data() + (lane >> 4) * kPlaneDoubles, 16 * w + (lane & 15));
   for (int w = 0; w < 2; w++)
-    for (int lane = 0; lane < 32; lane++) col_load_brev(s.regs[w][lane].xr, s.plane.data() + w * kHalfN, lane);
+    for (int lane = 0; lane < 32; lane++) col_load_brev(s.regs[w][lane].xr, s.plane.data() + w * kPlaneDoubles, lane);
   for (int w = 0; w < 2; w++)
-    for (int lane = 0; lane < 32; lane++) row_store(s.regs[w][lane].xi, s.plane.data() + (lane >> 4) * kHalfN, 16 * w + (lane & 15));
+    for (int lane = 0; lane < 32; lane++) row_store(s.regs[w][lane].xi, s.plane.data() + (lane >> 4) * kPlaneDoubles, 16 * w + (lane & 15));
   for (int w = 0; w < 2; w++)
-    for (int lane = 0; lane < 32; lane++) col_load_brev(s.regs[w][lane].xi, s.plane.data() + w * kHalfN, lane);
+    for (int lane = 0; lane < 32; lane++) col_load_brev(s.regs[w][lane].xi, s.plane.data() + w * kPlaneDoubles, lane);
   for (int w = 0; w < 2; w++)
     for (int lane = 0; lane < 32; lane++) fft32_inv(s.regs[w][lane].xr, s.regs[w][lane].xi);
 }
@@ -173,13 +173,13 @@ static void cmux_step_fused(Sample& s, const c2* fbsk, int i, uint32_t a) {
   for (int w = 0; w < 2; w++)
     for (int lane = 0; lane < 32; lane++) fwd_twiddle_inplace(s.regs[w][lane].xr, s.regs[w][lane].xi, g_tab_f, lane);
   for (int w = 0; w < 2; w++)
-    for (int lane = 0; lane < 32; lane++) col_store_brev(s.regs[w][lane].xr, s.plane.data() + w * kHalfN, lane);
+    for (int lane = 0; lane < 32; lane++) col_store_brev(s.regs[w][lane].xr, s.plane.data() + w * kPlaneDoubles, lane);
   for (int w = 0; w < 2; w++)
-    for (int lane = 0; lane < 32; lane++) row_load(s.regs[w][lane].xr, s.plane.data() + (lane >> 4) * kHalfN, 16 * w + (lane & 15));
+    for (int lane = 0; lane < 32; lane++) row_load(s.regs[w][lane].xr, s.plane.data() + (lane >> 4) * kPlaneDoubles, 16 * w + (lane & 15));
   for (int w = 0; w < 2; w++)
-    for (int lane = 0; lane < 32; lane++) col_store_brev(s.regs[w][lane].xi, s.plane.data() + w * kHalfN, lane);
+    for (int lane = 0; lane < 32; lane++) col_store_brev(s.regs[w][lane].xi, s.plane.data() + w * kPlaneDoubles, lane);
   for (int w = 0; w < 2; w++)
-    for (int lane = 0; lane < 32; lane++) row_load(s.regs[w][lane].xi, s.plane.data() + (lane >> 4) * kHalfN, 16 * w + (lane & 15));
+    for (int lane = 0; lane < 32; lane++) row_load(s.regs[w][lane].xi, s.plane.data() + (lane >> 4) * kPlaneDoubles, 16 * w + (lane & 15));
   for (int w = 0; w < 2; w++)
     for (int lane = 0; lane < 32; lane++) fft32_fwd_s12(s.regs[w][lane].xr, s.regs[w][lane].xi);
   emu_mid_block<0>(s, fbsk, i);
@@ -193,13 +193,13 @@ static void cmux_step_fused(Sample& s, const c2* fbsk, int i, uint32_t a) {
       inv_twiddle_inplace(R.xr, R.xi, g_tab_i, 16 * w + (lane & 15));
     }
   for (int w = 0; w < 2; w++)
-    for (int lane = 0; lane < 32; lane++) row_store(s.regs[w][lane].xr, s.plane.data() + (lane >> 4) * kHalfN, 16 * w + (lane & 15));
+    for (int lane = 0; lane < 32; lane++) row_store(s.regs[w][lane].xr, s.plane.data() + (lane >> 4) * kPlaneDoubles, 16 * w + (lane & 15));
   for (int w = 0; w < 2; w++)
-    for (int lane = 0; lane < 32; lane++) col_load_brev(s.regs[w][lane].xr, s.plane.data() + w * kHalfN, lane);
+    for (int lane = 0; lane < 32; lane++) col_load_brev(s.regs[w][lane].xr, s.plane.data() + w * kPlaneDoubles, lane);
   for (int w = 0; w < 2; w++)
-    for (int lane = 0; lane < 32; lane++) row_store(s.regs[w][lane].xi, s.plane.data() + (lane >> 4) * kHalfN, 16 * w + (lane & 15));
+    for (int lane = 0; lane < 32; lane++) row_store(s.regs[w][lane].xi, s.plane.data() + (lane >> 4) * kPlaneDoubles, 16 * w + (lane & 15));
   for (int w = 0; w < 2; w++)
-    for (int lane = 0; lane < 32; lane++) col_load_brev(s.regs[w][lane].xi, s.plane.data() + w * kHalfN, lane);
+    for (int lane = 0; lane < 32; lane++) col_load_brev(s.regs[w][lane].xi, s.plane.data() + w * kPlaneDoubles, lane);
   for (int w = 0; w < 2; w++)
     for (int lane = 0; lane < 32; lane++) {
       fft32_i2_head(s.regs[w][lane].xr, s.regs[w][lane].xi);

@@ -548,7 +548,7 @@ def test_server_key_in_the_references_own_form(client_key, server_key, gpu_key, 
 def test_options_are_per_context_and_checked(gpu_key, server_key):
     """fb_set_option / fb_get_option: defaults, round trip, unknown names and out-of-range values are errors, and a second
     context keeps its own values"""
-    assert gpu_key.get_option("br_variant") == 2 and gpu_key.get_option("ks_variant") == 1 and gpu_key.get_option("latency_threshold") == 296
+    assert gpu_key.get_option("br_variant") == 1 and gpu_key.get_option("ks_variant") == 1 and gpu_key.get_option("latency_threshold") == 296
     prev = gpu_key.set_option("latency_threshold", 100)
     assert prev == 296 and gpu_key.get_option("latency_threshold") == 100
     other = fb.ServerKey(server_key.ksk, server_key.bsk)
