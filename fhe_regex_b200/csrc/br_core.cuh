@@ -297,8 +297,16 @@ FB_HD double pbs_digit32_cvt(uint32_t diff) {
 template <int R, bool CVT = false>
 FB_HD void phaseA_slot(double& dr, double& di, const unsigned char* sm, uint32_t shp_off, uint32_t t0, const uint32_t* own) {
   const uint32_t ta = t0 + 128u * R, tb = t0 + 128u * (R + 32);
+#if defined(__CUDA_ARCH__)
+  // the kernel places the block so that sm + shp_off is 8 KiB aligned as an ABSOLUTE shared-memory address: the masked rotation
+  // offset is OR-ed into it (one LOP3 in front of the load instead of a LOP3 and an add)
+  const uint32_t base = (uint32_t)__cvta_generic_to_shared(sm) + shp_off;
+  uint32_t xa = *reinterpret_cast<const uint32_t*>(__cvta_shared_to_generic((ta & 8188u) | base));
+  uint32_t xb = *reinterpret_cast<const uint32_t*>(__cvta_shared_to_generic((tb & 8188u) | base));
+#else
   uint32_t xa = *reinterpret_cast<const uint32_t*>(sm + ((ta & 8188u) | shp_off));
   uint32_t xb = *reinterpret_cast<const uint32_t*>(sm + ((tb & 8188u) | shp_off));
+#endif
   if (ta & 8192u) xa = 0u - xa;
   if (tb & 8192u) xb = 0u - xb;
   if (CVT) {

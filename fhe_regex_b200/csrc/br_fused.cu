@@ -138,7 +138,10 @@ blind_rotate_fused_kernel(const c2* __restrict__ fbsk, const uint64_t* __restric
                           const uint32_t* __restrict__ lut_idx, uint64_t* __restrict__ out, const int32_t* __restrict__ out_rows,
                           const c2* __restrict__ tabs_g, int count, int stagger) {
   static_assert(2 * S <= 32, "64 TMEM columns per warp, 8 warps per lane quarter");
-  extern __shared__ __align__(128) unsigned char smem[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  // the block starts at the next 8 KiB boundary of the shared-memory window (the accumulator copies must sit at absolute
+  // multiples of 8 KiB: br_core.cuh::phaseA_slot); the launch reserves 8 KiB for this
+  unsigned char* smem = smem_raw + ((8192u - (smem_u32(smem_raw) & 8191u)) & 8191u);
   c2* stage = reinterpret_cast<c2*>(smem);                                             // [2][2][1024]
   uint32_t* shadow_all = reinterpret_cast<uint32_t*>(smem + kGgswBytes);                // [S][2][2048], every polynomial at a multiple of 8 KiB
   double* plane_all = reinterpret_cast<double*>(smem + kGgswBytes + (size_t)S * 16384);  // [S][2][kPlaneDoubles]
@@ -384,7 +387,7 @@ blind_rotate_fused_kernel(const c2* __restrict__ fbsk, const uint64_t* __restric
 template <int S, int V>
 static cudaError_t launch_fused_s(const c2* fbsk, const uint64_t* small, const uint64_t* luts, const uint32_t* lut_idx, uint64_t* out,
                                   const int32_t* out_rows, const c2* tabs, int count, int stagger, cudaStream_t st) {
-  const size_t smem = br_smem_bytes(S);
+  const size_t smem = br_smem_bytes(S) + 8192;   // + alignment of the block to an absolute 8 KiB boundary
   static PerDeviceOnce once;
   bool& configured = *once.slot();
   if (!configured) {
