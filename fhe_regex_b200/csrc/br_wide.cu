@@ -6,9 +6,9 @@
 // Replaces, like kernels.cu, the blind rotation under /root/reference/src/regex/execution.rs:76,93,110,143,173,190;
 // this variant exists because has_match (engine.rs:22-35) ends in levels of a few PBS whose cost is pure latency.
 //
-// Shared memory (209.6 KiB): two GGSW stages (2 x 64 KiB, cp.async.bulk; the copy of the next needed step is
-// issued at the top of the current one, a full step ahead) + two transform buffers [2][1024] complex (2 x 32 KiB,
-// Stockham ping-pong) + the accumulator [2][2048] u32 (16 KiB) + small tables.  Steps whose mask element
+// Shared memory (219 KiB): two GGSW stages (2 x 64 KiB, cp.async.bulk; the copy of the next needed step is
+// issued at the top of the current one, a full step ahead) + two transform buffers [2][1152] complex (2 x 36 KiB,
+// Stockham ping-pong, groups of 8 elements padded to 9: br_wide.cuh::LPad) + the accumulator [2][2048] u32 (16 KiB) + small tables.  Steps whose mask element
 // switches to 0 (all of them for trivial inputs) are skipped through a compacted step list.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -22,7 +22,8 @@ namespace fb {
 namespace {
 constexpr int kStageBytes = 4 * kHalfN * (int)sizeof(c2);  // 65536
 // kMacPrefetch (template parameter of the kernel): groups of 4 GGSW values a thread fetches before the pre-MAC barrier
-constexpr int kBufBytes = 2 * kHalfN * (int)sizeof(c2);    // 32768
+using WL = wide::LPad;                                     // padded transform buffers: every access [base + immediate]
+constexpr int kBufBytes = 2 * WL::kBuf * (int)sizeof(c2);  // 36864
 constexpr size_t kOffBufA = 2 * (size_t)kStageBytes;
 constexpr size_t kOffBufB = kOffBufA + kBufBytes;
 constexpr size_t kOffAcc = kOffBufB + kBufBytes;
@@ -102,8 +103,8 @@ blind_rotate_wide_kernel(const c2* __restrict__ fbsk, const uint64_t* __restrict
   const int n_steps = *n_steps_p;
 
   uint32_t* accp = acc + P * kN;
-  c2* bufA_p = bufA + P * kHalfN;
-  c2* bufB_p = bufB + P * kHalfN;
+  c2* bufA_p = bufA + P * WL::kBuf;
+  c2* bufB_p = bufB + P * WL::kBuf;
 
 #pragma unroll 1
   for (int n = 0; n < n_steps; n++) {
@@ -113,11 +114,11 @@ blind_rotate_wide_kernel(const c2* __restrict__ fbsk, const uint64_t* __restrict
     if (tid == 0 && n + 1 < n_steps) issue_ggsw(steps[n + 1], (n + 1) & 1);
     // The two polynomials only meet in the Fourier MAC: everywhere else a half (128 threads) synchronises on its
     // own named barrier, so one half's transform arithmetic overlaps the other half's shared-memory traffic.
-    wide::fwd_stage1(accp, own, a, t, tw, bufA_p);
+    wide::fwd_stage1<WL>(accp, own, a, t, tw, bufA_p);
     half_sync(P);
-    wide::fwd_stage2(bufA_p, bufB_p, t, tw);
+    wide::fwd_stage2<WL>(bufA_p, bufB_p, t, tw);
     half_sync(P);
-    wide::fwd_stage3(bufB_p, bufA_p, t);
+    wide::fwd_stage3<WL>(bufB_p, bufA_p, t);
     // the staged GGSW does not depend on the other warps: wait for it and fetch half of this thread's values before the
     // barrier, so that their shared-memory latency falls into the barrier wait
     mbar_wait(full_bar + (n & 1), (uint32_t)(n >> 1) & 1u);
@@ -125,7 +126,7 @@ blind_rotate_wide_kernel(const c2* __restrict__ fbsk, const uint64_t* __restrict
     c2 gpre[4 * (kMacPrefetch > 0 ? kMacPrefetch : 1)];
     wide::mac_prefetch<kMacPrefetch>(ggsw, P, t, gpre);
     __syncthreads();                              // both spectra complete
-    wide::mac_inv_stage1<kMacPrefetch>(bufA, bufA + kHalfN, ggsw, gpre, P, t, tw, bufB_p);
+    wide::mac_inv_stage1<kMacPrefetch, WL>(bufA, bufA + WL::kBuf, ggsw, gpre, P, t, tw, bufB_p);
     __syncthreads();                              // nobody reads bufA (or this GGSW stage) any more
     // the halves leave this barrier in phase; holding one back by a fraction of a stage makes its shared-memory
     // bursts fall into the other half's arithmetic for the six per-half stages until they meet again
@@ -133,11 +134,11 @@ blind_rotate_wide_kernel(const c2* __restrict__ fbsk, const uint64_t* __restrict
       const long long t0 = clock64();
       while (clock64() - t0 < (long long)skew_cycles) {}
     }
-    wide::inv_stage2(bufB_p, bufA_p, t, tw);
+    wide::inv_stage2<WL>(bufB_p, bufA_p, t, tw);
     half_sync(P);
-    wide::inv_stage3(bufA_p, bufB_p, t);
+    wide::inv_stage3<WL>(bufA_p, bufB_p, t);
     half_sync(P);
-    wide::phaseC_accumulate(bufB_p, t, own, accp);
+    wide::phaseC_accumulate<WL>(bufB_p, t, own, accp);
     half_sync(P);
   }
   __syncthreads();

@@ -42,6 +42,29 @@ struct Tw {
 };
 
 FB_HD int swz(int idx) { return idx ^ ((idx >> 3) & 7); }
+// Where element idx of a transform buffer lives.  Both layouts make every stage's 128-bit accesses conflict-free (a quarter-warp
+// either walks the low three bits of idx inside one group of 8, or walks the groups at a fixed low part).
+//   LSwz  XOR swizzle inside a buffer of 1024 elements: no extra memory (br_wide2.cu has none to spare), but an address is a
+//         LOP3 / shift / add chain per access, recomputed every step (the register file cannot hold 150 addresses);
+//   LPad  groups of 8 elements padded to 9 (idx + idx / 8, 1152 elements per polynomial): idx is (thread part) + (compile-time
+//         part), and so is its position -- every access of a stage is [one base register + immediate].
+#if defined(__CUDACC__)
+#define FB_HDM static __host__ __device__ __forceinline__
+#else
+#define FB_HDM static inline
+#endif
+// at2(a, c): position of element a + c, a the per-thread part and c the compile-time part of the index (in every use either c is a
+// multiple of 8 or a is and c < 8, so that (a + c) / 8 = a / 8 + c / 8)
+struct LSwz {
+  static constexpr int kBuf = 1024;
+  FB_HDM int at(int idx) { return idx ^ ((idx >> 3) & 7); }
+  FB_HDM int at2(int a, int c) { return at(a + c); }
+};
+struct LPad {
+  static constexpr int kBuf = 1152;
+  FB_HDM int at(int idx) { return idx + (idx >> 3); }
+  FB_HDM int at2(int a, int c) { return at(a) + c + (c >> 3); }
+};
 
 FB_HD c2 mk(double x, double y) {
   c2 r;
@@ -93,6 +116,7 @@ FB_HD void dft8(c2 (&x)[8]) {
    : (m) == 6 ? 0.92387953251128675613 : 0.98078528040323044913)
 
 // twist by exp(i pi m/16) per register, 8-point DFT, stage-1 twiddle (carries w^t), store
+template <class L = LSwz>
 FB_HD void fwd_stage1_core(c2 (&x)[8], int t, const c2 (&w1f)[8], c2* out) {
 #pragma unroll
   for (int m = 1; m < 8; m++) {
@@ -101,13 +125,15 @@ FB_HD void fwd_stage1_core(c2 (&x)[8], int t, const c2 (&w1f)[8], c2* out) {
   }
   dft8<false>(x);
 #pragma unroll
-  for (int k = 0; k < 8; k++) out[swz(8 * t + k)] = cmul(x[k], w1f[k]);
+  for (int k = 0; k < 8; k++) out[L::at2(8 * t, k)] = cmul(x[k], w1f[k]);
 }
-FB_HD void fwd_stage1_core(c2 (&x)[8], int t, const Tw& tw, c2* out) { fwd_stage1_core(x, t, tw.w1f, out); }
+template <class L = LSwz>
+FB_HD void fwd_stage1_core(c2 (&x)[8], int t, const Tw& tw, c2* out) { fwd_stage1_core<L>(x, t, tw.w1f, out); }
 
 // phase A + forward stage 1: digits of (acc X^a - acc) for coefficients j = t + 128 m and j + 1024.
 // own[2m], own[2m+1]: this thread's accumulator words of those coefficients (registers; the thread that rounds
 // coefficient j in phase C is the one that decomposes it here); accp: the shared copy, for the rotated reads
+template <class L = LSwz>
 FB_HD void fwd_stage1(const uint32_t* accp, const uint32_t (&own)[16], uint32_t a, int t, const c2 (&w1f)[8], c2* out) {
   c2 x[8];
 #pragma unroll
@@ -116,23 +142,26 @@ FB_HD void fwd_stage1(const uint32_t* accp, const uint32_t (&own)[16], uint32_t 
     x[m].x = pbs_digit32(rot_read32(accp, j, a) - own[2 * m]);
     x[m].y = pbs_digit32(rot_read32(accp, j + 1024u, a) - own[2 * m + 1]);
   }
-  fwd_stage1_core(x, t, w1f, out);
+  fwd_stage1_core<L>(x, t, w1f, out);
 }
+template <class L = LSwz>
 FB_HD void fwd_stage1(const uint32_t* accp, const uint32_t (&own)[16], uint32_t a, int t, const Tw& tw, c2* out) {
-  fwd_stage1(accp, own, a, t, tw.w1f, out);
+  fwd_stage1<L>(accp, own, a, t, tw.w1f, out);
 }
 
+template <class L = LSwz>
 FB_HD void fwd_stage2(const c2* in, c2* out, int t, const c2 (&w2f)[7]) {
   const int q = t & 7, p = t >> 3;
   c2 x[8];
 #pragma unroll
-  for (int r = 0; r < 8; r++) x[r] = in[swz(q + 8 * p + 128 * r)];
+  for (int r = 0; r < 8; r++) x[r] = in[L::at2(q + 8 * p, 128 * r)];
   dft8<false>(x);
-  out[swz(q + 64 * p)] = x[0];
+  out[L::at2(q + 64 * p, 0)] = x[0];
 #pragma unroll
-  for (int k = 1; k < 8; k++) out[swz(q + 64 * p + 8 * k)] = cmul(x[k], w2f[k - 1]);
+  for (int k = 1; k < 8; k++) out[L::at2(q + 64 * p, 8 * k)] = cmul(x[k], w2f[k - 1]);
 }
-FB_HD void fwd_stage2(const c2* in, c2* out, int t, const Tw& tw) { fwd_stage2(in, out, t, tw.w2f); }
+template <class L = LSwz>
+FB_HD void fwd_stage2(const c2* in, c2* out, int t, const Tw& tw) { fwd_stage2<L>(in, out, t, tw.w2f); }
 
 // stage-3 twiddles depend on p3 = t >> 6 only, which is warp-uniform: compile-time constants behind a uniform branch
 // forward W16^{p3 k} = exp(-i pi p3 k / 8); inverse exp(+i pi p3 k / 8) * w^{-64 (k & 1)} (the per-parity part of
@@ -146,23 +175,24 @@ FB_HD void fwd_stage2(const c2* in, c2* out, int t, const Tw& tw) { fwd_stage2(i
 #define FB_W3I_S(k) ((k) == 1 ? 0.290284677254462367636 : (k) == 2 ? 0.707106781186547524401 : (k) == 3 ? 0.881921264348355029713 \
                      : (k) == 5 ? 0.956940335732208864936 : (k) == 6 ? 0.707106781186547524401 : 0.471396736825997648556)
 
-template <int P3>
+template <int P3, class L = LSwz>
 FB_HD void fwd_stage3_p(const c2* in, c2* out, int q) {
   c2 x[8];
 #pragma unroll
-  for (int r = 0; r < 8; r++) x[r] = in[swz(q + 64 * P3 + 128 * r)];
+  for (int r = 0; r < 8; r++) x[r] = in[L::at2(q, 64 * P3 + 128 * r)];
   dft8<false>(x);
 #pragma unroll
   for (int k = 0; k < 8; k++) {
     c2 y = x[k];
     if (P3 == 1 && k == 4) y = rot90<false>(x[k]);
     else if (P3 == 1 && k != 0) y = cmul(x[k], mk(FB_W3_C(k), -FB_W3_S(k)));
-    out[swz(q + 512 * P3 + 64 * k)] = y;
+    out[L::at2(q, 512 * P3 + 64 * k)] = y;
   }
 }
+template <class L = LSwz>
 FB_HD void fwd_stage3(const c2* in, c2* out, int t) {
-  if ((t >> 6) == 0) fwd_stage3_p<0>(in, out, t & 63);
-  else fwd_stage3_p<1>(in, out, t & 63);
+  if ((t >> 6) == 0) fwd_stage3_p<0, L>(in, out, t & 63);
+  else fwd_stage3_p<1, L>(in, out, t & 63);
 }
 
 // forward stage 4 (a+b, a-b) of both polynomials + Fourier MAC with the staged GGSW + inverse stage 1.
@@ -182,7 +212,7 @@ FB_HD void mac_prefetch(const c2* ggsw, int qo, int t, c2 (&gpre)[4 * (NPRE > 0 
     gpre[4 * u + 3] = g1[k + 512];
   }
 }
-template <int NPRE>
+template <int NPRE, class L = LSwz>
 FB_HD void mac_inv_stage1(const c2* in0, const c2* in1, const c2* ggsw, const c2* gpre, int qo, int t, const c2 (&w1i)[7], c2* out) {
   c2 o[8];
   const c2* g0 = ggsw + (size_t)(0 * 2 + qo) * kHalfN;
@@ -190,8 +220,8 @@ FB_HD void mac_inv_stage1(const c2* in0, const c2* in1, const c2* ggsw, const c2
 #pragma unroll
   for (int u = 0; u < 4; u++) {
     const int k = t + 128 * u;
-    const c2 a0 = in0[swz(k)], b0 = in0[swz(k + 512)];
-    const c2 a1 = in1[swz(k)], b1 = in1[swz(k + 512)];
+    const c2 a0 = in0[L::at2(t, 128 * u)], b0 = in0[L::at2(t, 128 * u + 512)];
+    const c2 a1 = in1[L::at2(t, 128 * u)], b1 = in1[L::at2(t, 128 * u + 512)];
     const c2 x0l = cadd(a0, b0), x0h = csub(a0, b0), x1l = cadd(a1, b1), x1h = csub(a1, b1);
     const c2 gl0 = u < NPRE ? gpre[4 * u] : g0[k], gl1 = u < NPRE ? gpre[4 * u + 1] : g1[k];
     const c2 gh0 = u < NPRE ? gpre[4 * u + 2] : g0[k + 512], gh1 = u < NPRE ? gpre[4 * u + 3] : g1[k + 512];
@@ -201,47 +231,50 @@ FB_HD void mac_inv_stage1(const c2* in0, const c2* in1, const c2* ggsw, const c2
     o[u + 4].y = fb_fma(x1h.y, gh1.x, fb_fma(x1h.x, gh1.y, fb_fma(x0h.y, gh0.x, x0h.x * gh0.y)));
   }
   dft8<true>(o);
-  out[swz(8 * t)] = o[0];
+  out[L::at2(8 * t, 0)] = o[0];
 #pragma unroll
-  for (int k = 1; k < 8; k++) out[swz(8 * t + k)] = cmul(o[k], w1i[k - 1]);
+  for (int k = 1; k < 8; k++) out[L::at2(8 * t, k)] = cmul(o[k], w1i[k - 1]);
 }
-template <int NPRE>
+template <int NPRE, class L = LSwz>
 FB_HD void mac_inv_stage1(const c2* in0, const c2* in1, const c2* ggsw, const c2* gpre, int qo, int t, const Tw& tw, c2* out) {
-  mac_inv_stage1<NPRE>(in0, in1, ggsw, gpre, qo, t, tw.w1i, out);
+  mac_inv_stage1<NPRE, L>(in0, in1, ggsw, gpre, qo, t, tw.w1i, out);
 }
 
 // pointwise product variant for the negacyclic-product test (one polynomial, spectrum b in natural order)
+template <class L = LSwz>
 FB_HD void mul_inv_stage1(const c2* in0, const c2* spec, int t, const Tw& tw, c2* out) {
   c2 o[8];
 #pragma unroll
   for (int u = 0; u < 4; u++) {
     const int k = t + 128 * u;
-    const c2 a0 = in0[swz(k)], b0 = in0[swz(k + 512)];
+    const c2 a0 = in0[L::at2(t, 128 * u)], b0 = in0[L::at2(t, 128 * u + 512)];
     o[u] = cmul(cadd(a0, b0), spec[k]);
     o[u + 4] = cmul(csub(a0, b0), spec[k + 512]);
   }
   dft8<true>(o);
-  out[swz(8 * t)] = o[0];
+  out[L::at2(8 * t, 0)] = o[0];
 #pragma unroll
-  for (int k = 1; k < 8; k++) out[swz(8 * t + k)] = cmul(o[k], tw.w1i[k - 1]);
+  for (int k = 1; k < 8; k++) out[L::at2(8 * t, k)] = cmul(o[k], tw.w1i[k - 1]);
 }
 
+template <class L = LSwz>
 FB_HD void inv_stage2(const c2* in, c2* out, int t, const c2 (&w2i)[8]) {
   const int q = t & 7, p = t >> 3;
   c2 x[8];
 #pragma unroll
-  for (int r = 0; r < 8; r++) x[r] = in[swz(q + 8 * p + 128 * r)];
+  for (int r = 0; r < 8; r++) x[r] = in[L::at2(q + 8 * p, 128 * r)];
   dft8<true>(x);
 #pragma unroll
-  for (int k = 0; k < 8; k++) out[swz(q + 64 * p + 8 * k)] = cmul(x[k], w2i[k]);
+  for (int k = 0; k < 8; k++) out[L::at2(q + 64 * p, 8 * k)] = cmul(x[k], w2i[k]);
 }
-FB_HD void inv_stage2(const c2* in, c2* out, int t, const Tw& tw) { inv_stage2(in, out, t, tw.w2i); }
+template <class L = LSwz>
+FB_HD void inv_stage2(const c2* in, c2* out, int t, const Tw& tw) { inv_stage2<L>(in, out, t, tw.w2i); }
 
-template <int P3>
+template <int P3, class L = LSwz>
 FB_HD void inv_stage3_p(const c2* in, c2* out, int q) {
   c2 x[8];
 #pragma unroll
-  for (int r = 0; r < 8; r++) x[r] = in[swz(q + 64 * P3 + 128 * r)];
+  for (int r = 0; r < 8; r++) x[r] = in[L::at2(q, 64 * P3 + 128 * r)];
   dft8<true>(x);
 #pragma unroll
   for (int k = 0; k < 8; k++) {
@@ -252,21 +285,23 @@ FB_HD void inv_stage3_p(const c2* in, c2* out, int q) {
       if (k == 4) y = rot90<true>(x[k]);
       else if (k != 0) y = cmul(x[k], mk(FB_W3I_C(k), FB_W3I_S(k)));
     }
-    out[swz(q + 512 * P3 + 64 * k)] = y;
+    out[L::at2(q, 512 * P3 + 64 * k)] = y;
   }
 }
+template <class L = LSwz>
 FB_HD void inv_stage3(const c2* in, c2* out, int t) {
-  if ((t >> 6) == 0) inv_stage3_p<0>(in, out, t & 63);
-  else inv_stage3_p<1>(in, out, t & 63);
+  if ((t >> 6) == 0) inv_stage3_p<0, L>(in, out, t & 63);
+  else inv_stage3_p<1, L>(in, out, t & 63);
 }
 
 // inverse stage 4 + per-register untwist exp(-i pi m/16): torus increments of coefficients j = t + 128 m (re)
 // and j + 1024 (im); everything else of the untwist and the 1/1024 is already in the data
+template <class L = LSwz>
 FB_HD void inv_stage4(const c2* in, int t, uint32_t (&inc_re)[8], uint32_t (&inc_im)[8]) {
   c2 z[8];
 #pragma unroll
   for (int u = 0; u < 4; u++) {
-    const c2 a = in[swz(t + 128 * u)], b = in[swz(t + 128 * u + 512)];
+    const c2 a = in[L::at2(t, 128 * u)], b = in[L::at2(t, 128 * u + 512)];
     z[u] = cadd(a, b);
     z[u + 4] = csub(a, b);
   }
@@ -280,9 +315,10 @@ FB_HD void inv_stage4(const c2* in, int t, uint32_t (&inc_re)[8], uint32_t (&inc
   }
 }
 
+template <class L = LSwz>
 FB_HD void phaseC_accumulate(const c2* in, int t, uint32_t (&own)[16], uint32_t* accp) {
   uint32_t ire[8], iim[8];
-  inv_stage4(in, t, ire, iim);
+  inv_stage4<L>(in, t, ire, iim);
 #pragma unroll
   for (int m = 0; m < 8; m++) {
     const int j = t + 128 * m;

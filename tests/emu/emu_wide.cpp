@@ -9,15 +9,16 @@
 
 using namespace fb;
 using namespace fb::wide;
+using WL = fb::wide::LPad;   // the layout br_wide.cu uses (br_wide2.cu keeps LSwz: the GPU test compares the two bit for bit)
 
 namespace {
 struct Cta {
   std::vector<c2> tab;          // [kTabC2]
-  std::vector<c2> bufA, bufB;   // [2][1024]
+  std::vector<c2> bufA, bufB;   // [2][WL::kBuf]
   std::vector<uint32_t> acc;    // [2][2048] shared copy
   uint32_t own[256][16];        // registers: thread (P, t) owns coefficients t + 128m (+1024) of polynomial P
   Tw tw[256];
-  Cta() : tab(kTabC2), bufA(2 * kHalfN), bufB(2 * kHalfN), acc(2 * kN) {
+  Cta() : tab(kTabC2), bufA(2 * WL::kBuf), bufB(2 * WL::kBuf), acc(2 * kN) {
     make_wide_table(tab.data());
     for (int tid = 0; tid < 256; tid++) load_tw(tw[tid], tab.data(), tid & 127);
   }
@@ -25,12 +26,12 @@ struct Cta {
 
 // stages 2 and 3 of the forward transform of both polynomials: bufA -> bufB -> bufA (barriers between the loops)
 void forward_tail(Cta& c) {
-  for (int tid = 0; tid < 256; tid++) fwd_stage2(c.bufA.data() + (tid >> 7) * kHalfN, c.bufB.data() + (tid >> 7) * kHalfN, tid & 127, c.tw[tid]);
-  for (int tid = 0; tid < 256; tid++) fwd_stage3(c.bufB.data() + (tid >> 7) * kHalfN, c.bufA.data() + (tid >> 7) * kHalfN, tid & 127);
+  for (int tid = 0; tid < 256; tid++) fwd_stage2<WL>(c.bufA.data() + (tid >> 7) * WL::kBuf, c.bufB.data() + (tid >> 7) * WL::kBuf, tid & 127, c.tw[tid]);
+  for (int tid = 0; tid < 256; tid++) fwd_stage3<WL>(c.bufB.data() + (tid >> 7) * WL::kBuf, c.bufA.data() + (tid >> 7) * WL::kBuf, tid & 127);
 }
 void inverse_tail(Cta& c) {
-  for (int tid = 0; tid < 256; tid++) inv_stage2(c.bufB.data() + (tid >> 7) * kHalfN, c.bufA.data() + (tid >> 7) * kHalfN, tid & 127, c.tw[tid]);
-  for (int tid = 0; tid < 256; tid++) inv_stage3(c.bufA.data() + (tid >> 7) * kHalfN, c.bufB.data() + (tid >> 7) * kHalfN, tid & 127);
+  for (int tid = 0; tid < 256; tid++) inv_stage2<WL>(c.bufB.data() + (tid >> 7) * WL::kBuf, c.bufA.data() + (tid >> 7) * WL::kBuf, tid & 127, c.tw[tid]);
+  for (int tid = 0; tid < 256; tid++) inv_stage3<WL>(c.bufA.data() + (tid >> 7) * WL::kBuf, c.bufB.data() + (tid >> 7) * WL::kBuf, tid & 127);
 }
 }  // namespace
 
@@ -45,12 +46,12 @@ extern "C" void emu_wide_forward_torus(const uint64_t* polys /* [2][2048] */, c2
       x[m].x = (double)(int64_t)polys[P * kN + j] * (1.0 / 18446744073709551616.0);
       x[m].y = (double)(int64_t)polys[P * kN + j + 1024] * (1.0 / 18446744073709551616.0);
     }
-    fwd_stage1_core(x, t, c.tw[tid], c.bufA.data() + P * kHalfN);
+    fwd_stage1_core<WL>(x, t, c.tw[tid], c.bufA.data() + P * WL::kBuf);
   }
   forward_tail(c);
   for (int P = 0; P < 2; P++)
     for (int k = 0; k < 512; k++) {
-      const c2 a = c.bufA[P * kHalfN + swz(k)], b = c.bufA[P * kHalfN + swz(k + 512)];
+      const c2 a = c.bufA[P * WL::kBuf + WL::at(k)], b = c.bufA[P * WL::kBuf + WL::at(k + 512)];
       spec[P * kHalfN + k] = cadd(a, b);
       spec[P * kHalfN + k + 512] = csub(a, b);
     }
@@ -72,17 +73,17 @@ extern "C" void emu_wide_negacyclic_mul(const int64_t* a_int, const uint64_t* b_
       x[m].x = P == 0 ? (double)a_int[j] : 0.0;
       x[m].y = P == 0 ? (double)a_int[j + 1024] : 0.0;
     }
-    fwd_stage1_core(x, t, c.tw[tid], c.bufA.data() + P * kHalfN);
+    fwd_stage1_core<WL>(x, t, c.tw[tid], c.bufA.data() + P * WL::kBuf);
   }
   forward_tail(c);
   for (int tid = 0; tid < 256; tid++) {
     const int P = tid >> 7, t = tid & 127;
-    mul_inv_stage1(c.bufA.data() + P * kHalfN, spec.data(), t, c.tw[tid], c.bufB.data() + P * kHalfN);
+    mul_inv_stage1<WL>(c.bufA.data() + P * WL::kBuf, spec.data(), t, c.tw[tid], c.bufB.data() + P * WL::kBuf);
   }
   inverse_tail(c);
   std::fill(c.acc.begin(), c.acc.end(), 0u);
   memset(c.own, 0, sizeof c.own);
-  for (int tid = 0; tid < 256; tid++) phaseC_accumulate(c.bufB.data() + (tid >> 7) * kHalfN, tid & 127, c.own[tid], c.acc.data() + (tid >> 7) * kN);
+  for (int tid = 0; tid < 256; tid++) phaseC_accumulate<WL>(c.bufB.data() + (tid >> 7) * WL::kBuf, tid & 127, c.own[tid], c.acc.data() + (tid >> 7) * kN);
   for (int j = 0; j < kN; j++) out[j] = (uint64_t)c.acc[j] << 32;
   delete &c;
 }
@@ -106,12 +107,12 @@ extern "C" void emu_wide_blind_rotate(const c2* fbsk, const uint64_t* small, con
     const uint32_t a = modswitch(small[i]) & 4095u;
     if (small[i] == 0 || a == 0) continue;
     const c2* ggsw = fbsk + (size_t)i * 4 * kHalfN;
-    for (int tid = 0; tid < 256; tid++) fwd_stage1(c.acc.data() + (tid >> 7) * kN, c.own[tid], a, tid & 127, c.tw[tid], c.bufA.data() + (tid >> 7) * kHalfN);
+    for (int tid = 0; tid < 256; tid++) fwd_stage1<WL>(c.acc.data() + (tid >> 7) * kN, c.own[tid], a, tid & 127, c.tw[tid], c.bufA.data() + (tid >> 7) * WL::kBuf);
     forward_tail(c);
     for (int tid = 0; tid < 256; tid++)
-      mac_inv_stage1<0>(c.bufA.data(), c.bufA.data() + kHalfN, ggsw, nullptr, tid >> 7, tid & 127, c.tw[tid], c.bufB.data() + (tid >> 7) * kHalfN);
+      mac_inv_stage1<0, WL>(c.bufA.data(), c.bufA.data() + WL::kBuf, ggsw, nullptr, tid >> 7, tid & 127, c.tw[tid], c.bufB.data() + (tid >> 7) * WL::kBuf);
     inverse_tail(c);
-    for (int tid = 0; tid < 256; tid++) phaseC_accumulate(c.bufB.data() + (tid >> 7) * kHalfN, tid & 127, c.own[tid], c.acc.data() + (tid >> 7) * kN);
+    for (int tid = 0; tid < 256; tid++) phaseC_accumulate<WL>(c.bufB.data() + (tid >> 7) * WL::kBuf, tid & 127, c.own[tid], c.acc.data() + (tid >> 7) * kN);
   }
   for (int j = 0; j < 2 * kN; j++) acc_out[j] = (uint64_t)c.acc[j] << 32;
   delete &c;
