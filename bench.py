@@ -202,6 +202,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-match", action="store_true")
     ap.add_argument("--cpu-samples", type=int, default=0)
+    ap.add_argument("--option", action="append", default=[], metavar="NAME=VALUE", help="fb_set_option on the context (profiling / A-B runs)")
     args = ap.parse_args()
 
     # exactly ONE line on stdout: libraries (NCCL prints its version banner to stdout) get stderr instead
@@ -230,6 +231,9 @@ def main():
     ksk, bsk = fb.keygen_server_raw(ck, seed=0)       # ServerKey::new analogue, replica on every rank
     sk = fb.ServerKey(ksk, bsk, device=local_rank)
     del ksk, bsk
+    for ov in args.option:
+        name, _, val = ov.partition("=")
+        sk.set_option(name, int(val))
     q = sk.pbs_quantum()
     B = args.batch if args.batch > 0 else 48 * q
     luts_np, fs = lut_table()
@@ -337,7 +341,10 @@ def main():
                        "batch_per_gpu": B, "global_batch": B * world, "luts": int(luts_np.shape[0]),
                        "l2": "inputs+outputs %.0f MB per step > 126 MB L2; keys (109 MB) are re-read by design" % (2 * B * BIG * 8 / 1e6),
                        "parallelism": "replicated keys, batch sharded x%d" % world},
-            "roofline": {"kernel": "blind_rotate_fused_kernel<4, 1> (br_fused.cu)", "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+            "roofline": {"kernel": "blind_rotate_fused_kernel<%d, %d> (br_fused.cu)" % (
+                             sk.get_option("br_samples"),
+                             (sk.get_option("br_variant") - 1) | (8 if sk.get_option("br_planes") == 2 and sk.get_option("br_samples") == 4 else 0)
+                             | (64 if sk.get_option("br_planes") == 3 and sk.get_option("br_samples") == 4 else 0)), "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak if fp64_peak else None, "traffic": BR_TRAFFIC_MEASURED.get(B),
                          "traffic_unit": "B/launch (ncu dram read+write, profiles/r02_traffic_bench_batch.csv)",
                          "algorithmic_bytes": BSK_BYTES + B * (SMALL + BIG) * 8 + int(luts_np.nbytes),

@@ -279,12 +279,15 @@ int fb_run_blind_rotate(fb_ctx* ctx, const uint64_t* d_small, const uint64_t* d_
   if (count <= narrow_max) {
     e = narrow(d_small, d_lut_idx, d_out, d_out_rows, count);
   } else {
-    const int q = ctx->quantum;
+    // 6 PBS per CTA (fused body only, option "br_samples") once the batch is wider than a wave of 4 per SM
+    const int S = (ctx->br_samples == 6 && ctx->br_variant >= 1 && count > 4 * ctx->sms) ? 6 : fb::br_samples_per_cta();
+    const int q = ctx->sms * S;
     const int tail = (q > 0) ? count % q : 0;
     const int head = (tail > 0 && tail <= narrow_max) ? count - tail : count;
-    // the fused body is built for 4 PBS per SM: batches that do not fill the GPU at that width keep the phase-by-phase body
-    const bool fused = ctx->br_variant >= 1 && head > 3 * (q / fb::br_samples_per_cta());
-    e = fused ? fb::launch_blind_rotate_fused(ctx->d_fbsk, ctx->d_fbsk_lm, d_small, d_luts, d_lut_idx, d_out, d_out_rows, ctx->d_tabs, head, ctx->br_variant - 1, ctx->br_stagger, ctx->stream)
+    // the fused body is built for full SMs: batches that do not fill the GPU at 4 per SM keep the phase-by-phase body
+    const bool fused = ctx->br_variant >= 1 && head > 3 * ctx->sms;
+    const int fv = (ctx->br_variant - 1) | (ctx->br_barriers ? 4 : 0) | ((ctx->br_planes == 2 && S == 4 && ctx->br_variant <= 2) ? 8 : 0) | ((ctx->br_planes == 3 && S == 4 && ctx->br_variant <= 2) ? 64 : 0);
+    e = fused ? fb::launch_blind_rotate_fused(ctx->d_fbsk, ctx->d_fbsk_lm, d_small, d_luts, d_lut_idx, d_out, d_out_rows, ctx->d_tabs, head, fv, ctx->br_stagger | (ctx->br_stagger_groups << 24), S, ctx->stream)
               : fb::launch_blind_rotate(ctx->d_fbsk, d_small, d_luts, d_lut_idx, d_out, d_out_rows, ctx->d_tabs, head, ctx->stream);
     if (e == cudaSuccess && head < count)
       e = narrow(d_small + (size_t)head * FB_LWE_SMALL_WORDS, d_lut_idx + head, d_out_rows ? d_out : d_out + (size_t)head * FB_LWE_BIG_WORDS,
@@ -353,6 +356,10 @@ const OptionDesc kOptions[] = {
     {"wide_pair", 0, 2},                    // latency kernel with two PBS per CTA: 0 never, 1 for batches between one and two waves of SMs, 2 for every narrow batch
     {"wide_pair_prefetch", 0, 2},           // pair kernel: GGSW groups fetched before the pre-MAC barrier
     {"wide_pair_offset", 0, 100000},        // pair kernel: cycles the second sample of a CTA starts late
+    {"br_samples", 4, 6},                   // fused throughput kernel: PBS per CTA, 4 or 6 (6: transpose planes inside the accumulator copies)
+    {"br_stagger_groups", 0, 1},            // 1: "br_stagger" delays the odd samples of a CTA only (two scheduler groups, one instruction stream per scheduler)
+    {"br_planes", 1, 3},                    // fused throughput kernel at 4 PBS per CTA: 2 = a transpose plane per component (one barrier per transpose)
+    {"br_barriers", 0, 1},                  // fused throughput kernel: 1 keeps the two per-step barriers that are not needed (A/B measurements)
     {"dist_shard_min", 0, 1 << 30},         // fb_has_match_dist: levels of at most this many PBS are computed by every rank instead of being sharded (default: the SM count)
 };
 int64_t* option_slot(fb_ctx* ctx, const char* name, int64_t& shadow, int& which) {
@@ -372,7 +379,11 @@ int64_t* option_slot(fb_ctx* ctx, const char* name, int64_t& shadow, int& which)
         case 9: shadow = ctx->wide_pair; break;
         case 10: shadow = ctx->wide_pair_prefetch; break;
         case 11: shadow = ctx->wide_pair_offset; break;
-        case 12: shadow = ctx->dist_shard_min; break;
+        case 12: shadow = ctx->br_samples; break;
+        case 13: shadow = ctx->br_stagger_groups; break;
+        case 14: shadow = ctx->br_planes; break;
+        case 15: shadow = ctx->br_barriers; break;
+        case 16: shadow = ctx->dist_shard_min; break;
       }
       return &shadow;
     }
@@ -408,7 +419,15 @@ extern "C" int fb_set_option(fb_ctx* ctx, const char* name, int64_t value) {
     case 9: ctx->wide_pair = (int)value; break;
     case 10: ctx->wide_pair_prefetch = (int)value; break;
     case 11: ctx->wide_pair_offset = (int)value; break;
-    case 12: ctx->dist_shard_min = (int)value; break;
+    case 12:
+      if (value == 5) return fb_fail(ctx, FB_ERR_ARG, "br_samples is 4 or 6");
+      ctx->br_samples = (int)value;
+      ctx->quantum = ctx->sms * ctx->br_samples;
+      break;
+    case 13: ctx->br_stagger_groups = (int)value; break;
+    case 14: ctx->br_planes = (int)value; break;
+    case 15: ctx->br_barriers = (int)value; break;
+    case 16: ctx->dist_shard_min = (int)value; break;
   }
   return FB_OK;
 }

@@ -274,6 +274,135 @@ FB_HD void col_load_brev(double (&x)[32], const double* plane_p, int lane) {
   }
 }
 
+// ---- planes aliased into the accumulator copies (blind_rotate_fused_kernel with more than 4 PBS per SM) --------
+// Between phase A (last rotated read of a step) and phase C (which rewrites every word) the 8 KiB shared-memory copy of a
+// polynomial's accumulator holds nothing that is read again, and the plane of polynomial p is written by the warp that owns
+// polynomial p only (column side) before anybody reads it.  The plane of polynomial p therefore lives INSIDE the accumulator
+// copy of polynomial p: rows 0..29 (30 x 272 = 8160 bytes) in the copy itself, rows 30 and 31 in a 640-byte overflow block,
+// at +96 and +368 of a 128-byte aligned address -- the 16-byte bank groups 6 and 7 they have in the contiguous layout, so the
+// quarter-warp that holds rows 24..31 stays conflict-free.  Shared memory per PBS drops from 33 KiB to 17.25 KiB.
+// Pointer arguments: `main` = the polynomial's accumulator copy as doubles, `ovf` = its overflow block + 96 bytes.
+constexpr int kPlaneMainRows = 30;
+constexpr int kPlaneOvfBytes = 640;
+constexpr int kPlaneOvfLead = 96;
+FB_HD double* plane_al_row(double* main, double* ovf, int k1) {
+  return k1 < kPlaneMainRows ? main + k1 * kPlaneRow : ovf + (k1 - kPlaneMainRows) * kPlaneRow;
+}
+FB_HD void col_store_brev_al(const double (&x)[32], double* main_l, double* ovf_l) {   // both with the lane folded in
+#pragma unroll
+  for (int q = 0; q < 32; q++) {
+    const int k1 = brev5(q);
+    if (k1 < kPlaneMainRows) main_l[k1 * kPlaneRow] = x[q];
+    else ovf_l[(k1 - kPlaneMainRows) * kPlaneRow] = x[q];
+  }
+}
+FB_HD void col_load_brev_al(double (&x)[32], const double* main_l, const double* ovf_l) {
+#pragma unroll
+  for (int q = 0; q < 32; q++) {
+    const int k1 = brev5(q);
+    x[q] = k1 < kPlaneMainRows ? main_l[k1 * kPlaneRow] : ovf_l[(k1 - kPlaneMainRows) * kPlaneRow];
+  }
+}
+// row side: row_load(x, row, 0) / row_store(x, row, 0) with row = plane_al_row(main of pp, ovf of pp, k1)
+
+// ---- full inter-pass twiddle tables (blind_rotate_fused_kernel, V & 64) ---------------------------------------------------
+// The lo x hi rebuild costs 28 complex products = 112 FP64 instructions per direction, per thread and per CMUX step.  With the
+// planes inside the accumulator copies there is room for both full tables (2 x 16 KiB): the kernel builds them ONCE per launch
+// with the very same two-FMA products (fb_full_twiddle), so the values -- and therefore the outputs -- are bit-identical.
+FB_HD c2 fb_full_twiddle(const c2* tab, int e, int x) {   // entry e = 4h + l of tab_f (x = lane) or tab_i (x = k1)
+  const int h = e >> 2, l = e & 3;
+  const c2 lo = tab[l * 32 + x];
+  if (h == 0) return lo;
+  const c2 hi = tab[(4 + h) * 32 + x];
+  c2 t;
+  t.x = fb_fma(lo.x, hi.x, -(lo.y * hi.y));
+  t.y = fb_fma(lo.x, hi.y, lo.y * hi.x);
+  return t;
+}
+// forward: register q (row k1 = brev5(q)) *= full_f[k1][lane]
+FB_HD void fwd_twiddle_full(double (&xr)[32], double (&xi)[32], const c2* full_f_lane) {
+#pragma unroll
+  for (int k1 = 0; k1 < 32; k1++) {
+    const int q = brev5(k1);
+    const c2 t = full_f_lane[k1 * 32];
+    const double yr = fb_fma(xr[q], t.x, -(xi[q] * t.y));
+    xi[q] = fb_fma(xr[q], t.y, xi[q] * t.x);
+    xr[q] = yr;
+  }
+}
+// inverse: register c *= full_i[c][k1]
+FB_HD void inv_twiddle_full(double (&xr)[32], double (&xi)[32], const c2* full_i_k1) {
+#pragma unroll
+  for (int c = 0; c < 32; c++) {
+    const c2 t = full_i_k1[c * 32];
+    const double yr = fb_fma(xr[c], t.x, -(xi[c] * t.y));
+    xi[c] = fb_fma(xr[c], t.y, xi[c] * t.x);
+    xr[c] = yr;
+  }
+}
+
+// ---- both planes at once ("dual": the real plane inside the accumulator copy, the imaginary plane in a buffer of its own) ----
+// With a plane per component a transpose needs ONE two-warp barrier (stores | loads) instead of three, and the stores of an
+// element can be issued as soon as its inter-pass twiddle product exists: they drain while the FP64 pipe works on the next
+// products (the store side of shared memory, 128 B/cycle/SM, is what the split transposes waited for).
+// forward: fwd_twiddle_inplace + col_store_brev_al(re) + col_store_brev(im)
+FB_HD void fwd_twiddle_col_store(double (&xr)[32], double (&xi)[32], const c2* tab_f, int lane, double* re_main_l, double* re_ovf_l, double* im_l) {
+  c2 lo[4];
+#pragma unroll
+  for (int l = 0; l < 4; l++) lo[l] = tab_f[l * 32 + lane];
+#pragma unroll
+  for (int h = 0; h < 8; h++) {
+    const c2 hi = tab_f[(4 + h) * 32 + lane];
+#pragma unroll
+    for (int l = 0; l < 4; l++) {
+      const int q = brev5(4 * h + l);
+      const int k1 = 4 * h + l;   // = brev5(q)
+      double tr = lo[l].x, ti = lo[l].y;
+      if (h != 0) {
+        tr = fb_fma(lo[l].x, hi.x, -(lo[l].y * hi.y));
+        ti = fb_fma(lo[l].x, hi.y, lo[l].y * hi.x);
+      }
+      const double yr = fb_fma(xr[q], tr, -(xi[q] * ti));
+      const double yi = fb_fma(xr[q], ti, xi[q] * tr);
+      if (k1 < kPlaneMainRows) re_main_l[k1 * kPlaneRow] = yr;
+      else re_ovf_l[(k1 - kPlaneMainRows) * kPlaneRow] = yr;
+      im_l[k1 * kPlaneRow] = yi;
+    }
+  }
+}
+// inverse: inv_twiddle_inplace + row_store(re) + row_store(im); rows as 128-bit pairs of columns
+FB_HD void inv_twiddle_row_store(double (&xr)[32], double (&xi)[32], const c2* tab_i, int k1, double* re_row, double* im_row) {
+  c2 lo[4];
+#pragma unroll
+  for (int l = 0; l < 4; l++) lo[l] = tab_i[l * 32 + k1];
+  c2* rr = reinterpret_cast<c2*>(re_row);
+  c2* ri = reinterpret_cast<c2*>(im_row);
+#pragma unroll
+  for (int h = 0; h < 8; h++) {
+    const c2 hi = tab_i[(4 + h) * 32 + k1];
+    double yr[4], yi[4];
+#pragma unroll
+    for (int l = 0; l < 4; l++) {
+      const int c = 4 * h + l;
+      double tr = lo[l].x, ti = lo[l].y;
+      if (h != 0) {
+        tr = fb_fma(lo[l].x, hi.x, -(lo[l].y * hi.y));
+        ti = fb_fma(lo[l].x, hi.y, lo[l].y * hi.x);
+      }
+      yr[l] = fb_fma(xr[c], tr, -(xi[c] * ti));
+      yi[l] = fb_fma(xr[c], ti, xi[c] * tr);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      c2 a, b;
+      a.x = yr[2 * u]; a.y = yr[2 * u + 1];
+      b.x = yi[2 * u]; b.y = yi[2 * u + 1];
+      rr[2 * h + u] = a;
+      ri[2 * h + u] = b;
+    }
+  }
+}
+
 // ---- fused CMUX body (blind_rotate_fused_kernel, br_fused.cu) ------------------------------------------
 // The same arithmetic as above cut into pieces that interleave in program order: the decomposition of slot r
 // (shared-memory reads + integer work) with the butterflies of pass 1 that its digits make computable; the

@@ -49,9 +49,13 @@ struct fb_ctx {
   int wide_pair = 1;           // 1: narrow batches wider than the SM count take two PBS per CTA (br_wide2.cu); 2: every narrow batch does (tests); 0: never (option "wide_pair")
   int wide_pair_offset = 0;    // pair kernel: cycles the second sample of a CTA starts late (option "wide_pair_offset")
   int wide_pair_prefetch = 1;  // pair kernel: GGSW groups fetched before the pre-MAC barrier (option "wide_pair_prefetch")
-  int br_variant = 1;          // throughput blind rotation at 4 PBS per SM: 0 = phase-by-phase body (kernels.cu), 1 = fused body (br_fused.cu), 2 = fused + digits through I2F
+  int br_variant = 2;          // throughput blind rotation at 4 PBS per SM: 0 = phase-by-phase body (kernels.cu), 1 = fused body (br_fused.cu), 2 = fused + digits through I2F
   int ks_variant = 1;          // keyswitch GEMM: 0 = mma.sync (ks_kernels.cu), 1 = tcgen05 (ks_umma.cu) (option "ks_variant")
   int sms = 148;               // multiprocessors of the device
+  int br_samples = 4;          // fused throughput kernel: PBS per CTA, 4 or 6 (option "br_samples"); quantum follows
+  int br_stagger_groups = 0;   // 1: the skew goes to the odd samples only (option "br_stagger_groups")
+  int br_planes = 2;           // 2: a transpose plane per component in the fused kernel at 4 PBS per CTA (option "br_planes")
+  int br_barriers = 0;         // fused throughput kernel: 1 keeps two unneeded barriers per step (option "br_barriers", A/B only)
   int br_stagger = 0;          // fused throughput kernel: start skew between the samples of a CTA, cycles per sample index (option "br_stagger")
   bool plan_absorb = true;     // false: reference-shaped plan (option "plan_reference_shaped" = 1)
   bool plan_timing = false;    // planner phase times on stderr (option "plan_timing")

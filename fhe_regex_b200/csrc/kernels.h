@@ -23,7 +23,7 @@ cudaError_t launch_blind_rotate(const c2* fbsk, const uint64_t* small, const uin
 // variant: bit 0 digits through I2F, bit 1 Fourier key of the step staged in tensor memory (reads fbsk_lm, the key re-ordered by
 // launch_fbsk_lane_major)
 cudaError_t launch_blind_rotate_fused(const c2* fbsk, const c2* fbsk_lm, const uint64_t* small, const uint64_t* luts, const uint32_t* lut_idx,
-                                      uint64_t* out, const int32_t* out_rows, const c2* tabs, int count, int variant, int stagger, cudaStream_t st);
+                                      uint64_t* out, const int32_t* out_rows, const c2* tabs, int count, int variant, int stagger, int samples, cudaStream_t st);
 cudaError_t launch_fbsk_lane_major(const c2* fbsk, c2* fbsk_lm, cudaStream_t st);
 // latency variant: one PBS per CTA (br_wide.cu)
 size_t br_wide_table_bytes();

@@ -548,7 +548,7 @@ def test_server_key_in_the_references_own_form(client_key, server_key, gpu_key, 
 def test_options_are_per_context_and_checked(gpu_key, server_key):
     """fb_set_option / fb_get_option: defaults, round trip, unknown names and out-of-range values are errors, and a second
     context keeps its own values"""
-    assert gpu_key.get_option("br_variant") == 1 and gpu_key.get_option("ks_variant") == 1 and gpu_key.get_option("latency_threshold") == 296
+    assert gpu_key.get_option("br_variant") == 2 and gpu_key.get_option("br_planes") == 2 and gpu_key.get_option("br_samples") == 4 and gpu_key.get_option("ks_variant") == 1 and gpu_key.get_option("latency_threshold") == 296
     prev = gpu_key.set_option("latency_threshold", 100)
     assert prev == 296 and gpu_key.get_option("latency_threshold") == 100
     other = fb.ServerKey(server_key.ksk, server_key.bsk)
@@ -596,3 +596,36 @@ def test_throughput_blind_rotation_variants(variant, client_key, server_key, gpu
     err = tfhe.torus_err(ph, exp << np.uint64(59))
     assert [fck.decrypt_block(out[i]) for i in (0, 1, 63, 64, n - 2, n - 1)] == [int(exp[i]) for i in (0, 1, 63, 64, n - 2, n - 1)]
     assert np.abs(err).max() < PBS_ERR_MAX and err.std() < PBS_ERR_STD_MAX, (variant, err.std())
+
+
+def test_throughput_blind_rotation_layouts_bit_identical(client_key, gpu_key, fck):
+    """round 2, second half: the fused throughput kernel with 6 PBS per CTA (transpose planes inside the accumulator copies),
+    with a plane per component (one barrier per transpose), with full twiddle tables built once per launch, and with the two
+    unneeded barriers back -- all the same arithmetic in the same order: outputs bit-identical to the default layout"""
+    n = 6 * 148 + 5
+    msgs = np.arange(n) % 16
+    base = tfhe.encrypt_batch(client_key, msgs[:64], seed=52)
+    cts = np.ascontiguousarray(np.tile(base, ((n + 63) // 64, 1))[:n])
+    f = lambda x: (7 * x + 2) % 16
+    lut = fb.make_lut(f)
+    idx = np.zeros(n, dtype=np.uint32)
+    names = ("br_variant", "br_samples", "br_planes", "br_barriers", "br_stagger", "br_stagger_groups")
+    saved = [gpu_key.get_option(k) for k in names]
+    prev_lat = gpu_key.set_latency_threshold(0)
+    try:
+        outs = {}
+        for cfg in ((1, 4, 1, 0, 0, 0), (1, 4, 1, 1, 0, 0), (1, 4, 2, 0, 0, 0), (1, 4, 3, 0, 0, 0), (1, 6, 1, 0, 0, 0), (1, 6, 1, 0, 3000, 1),
+                    (2, 4, 1, 0, 0, 0), (2, 4, 2, 0, 0, 0), (2, 4, 3, 0, 0, 0), (2, 6, 1, 0, 0, 0)):
+            for k, v in zip(names, cfg):
+                gpu_key.set_option(k, v)
+            outs[cfg] = gpu_key.pbs(cts, lut[None], idx)
+    finally:
+        for k, v in zip(names, saved):
+            gpu_key.set_option(k, v)
+        gpu_key.set_latency_threshold(prev_lat)
+    for cfg, out in outs.items():
+        ref = outs[(cfg[0], 4, 1, 0, 0, 0)]
+        assert (out == ref).all(), cfg
+    out = outs[(1, 6, 1, 0, 0, 0)]
+    for i in (0, 1, 63, 64, 591, 592, 887, 888, n - 1):
+        assert fck.decrypt_block(out[i]) == f(int(msgs[i % 64]))

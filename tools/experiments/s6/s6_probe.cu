@@ -138,34 +138,16 @@ blind_rotate_fused_kernel(const c2* __restrict__ fbsk, const uint64_t* __restric
                           const uint32_t* __restrict__ lut_idx, uint64_t* __restrict__ out, const int32_t* __restrict__ out_rows,
                           const c2* __restrict__ tabs_g, int count, int stagger) {
   static_assert(2 * S <= 32, "64 TMEM columns per warp, 8 warps per lane quarter");
-  // DUAL (V & 8, 4 PBS per CTA): a plane per component -- the real plane inside the accumulator copy, the imaginary plane in a
-  // buffer of its own; one barrier per transpose.  AL: the (real) transpose planes live inside the accumulator copies
-  // (br_core.cuh, "planes aliased"): more than 4 PBS per CTA, or DUAL.
-  constexpr bool DUAL = (V & 8) != 0;
-  constexpr bool FULLTAB = (V & 64) != 0;   // full inter-pass twiddle tables in shared memory (built once per launch)
-  constexpr bool AL = S > 4 || DUAL || FULLTAB;
-  static_assert(!(FULLTAB && DUAL), "no shared memory for both");
-  static_assert(!(S > 4 && (V & 2)), "the tensor-memory key uses the columns of the third group of accumulators");
-  static_assert(!DUAL || S <= 4, "no shared memory for imaginary planes beyond 4 PBS per CTA");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // the block starts at the next 8 KiB boundary of the shared-memory window (the accumulator copies must sit at absolute
   // multiples of 8 KiB: br_core.cuh::phaseA_slot); the launch reserves 8 KiB for this
-  const uint32_t pad = (8192u - (smem_u32(smem_raw) & 8191u)) & 8191u;
-  unsigned char* smem = smem_raw + pad;
+  unsigned char* smem = smem_raw + ((8192u - (smem_u32(smem_raw) & 8191u)) & 8191u);
   c2* stage = reinterpret_cast<c2*>(smem);                                             // [2][2][1024]
   uint32_t* shadow_all = reinterpret_cast<uint32_t*>(smem + kGgswBytes);                // [S][2][2048], every polynomial at a multiple of 8 KiB
-  double* plane_all = reinterpret_cast<double*>(smem + kGgswBytes + (size_t)S * 16384);  // [S][2][kPlaneDoubles]; AL: [S][2] overflow blocks
-  constexpr size_t kPlaneBytes = AL ? (size_t)kPlaneOvfBytes : kPlaneDoubles * sizeof(double);
-  double* implane_all = reinterpret_cast<double*>(smem + kGgswBytes + (size_t)S * (16384 + 2 * kPlaneBytes));   // DUAL: [S][2][kPlaneDoubles]
-  constexpr size_t kImBytes = DUAL ? kPlaneDoubles * sizeof(double) : 0;
-  c2* tab_f = reinterpret_cast<c2*>(smem + kGgswBytes + (size_t)S * (16384 + 2 * kPlaneBytes + 2 * kImBytes));   // [12][32]
-  constexpr int kTabRows = FULLTAB ? 32 : kTabEntries;
-  c2* tab_i = tab_f + kTabRows * 32;                                                    // [12][32]; FULLTAB: both [32][32]
-  // the small arrays go into the alignment gap in front of the block when it is large enough (DUAL needs the room: the block
-  // plus a worst-case gap would not fit the 227 KiB of a CTA otherwise)
-  constexpr uint32_t kTailBytes = (uint32_t)S * 768u * 2u + 768u + 64u;
-  unsigned char* tail = (DUAL && pad >= kTailBytes) ? smem_raw : reinterpret_cast<unsigned char*>(tab_i + kTabRows * 32);
-  uint16_t* at_all = reinterpret_cast<uint16_t*>(tail);                                 // [S][768]
+  double* plane_all = reinterpret_cast<double*>(smem + kGgswBytes + (size_t)S * 16384);  // [S][2][kPlaneDoubles]
+  c2* tab_f = reinterpret_cast<c2*>(smem + kGgswBytes + (size_t)S * (16384 + 2 * kPlaneDoubles * sizeof(double)));   // [12][32]
+  c2* tab_i = tab_f + kTabEntries * 32;                                                 // [12][32]
+  uint16_t* at_all = reinterpret_cast<uint16_t*>(tab_i + kTabEntries * 32);             // [S][768]
   uint8_t* need = reinterpret_cast<uint8_t*>(at_all + S * 768);                         // [768]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(need + 768);                         // GGSW bytes have landed
   uint64_t* tkey_bar = full_bar + 1;                                                    // (V & 2) GGSW copied into tensor memory
@@ -173,7 +155,6 @@ blind_rotate_fused_kernel(const c2* __restrict__ fbsk, const uint64_t* __restric
   uint32_t* done_cnt = reinterpret_cast<uint32_t*>(macdone_bar + 1);                    // warps done with the stage
   uint32_t* tmem_slot = done_cnt + 1;
   constexpr bool kTKey = (V & 2) != 0;
-  constexpr bool kRedundantBarriers = (V & 4) != 0;   // the two barriers per step that round 2 found unnecessary (A/B only)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int s = warp >> 1, w = warp & 1;
@@ -181,14 +162,7 @@ blind_rotate_fused_kernel(const c2* __restrict__ fbsk, const uint64_t* __restric
   const bool active = sample < count;
   const uint32_t n_warps_active = 2u * (uint32_t)min(S, count - (int)blockIdx.x * S);
 
-  if (FULLTAB) {
-    for (int t = tid; t < 1024; t += 64 * S) {
-      tab_f[t] = fb_full_twiddle(tabs_g, t >> 5, t & 31);
-      tab_i[t] = fb_full_twiddle(tabs_g + kTabEntries * 32, t >> 5, t & 31);
-    }
-  } else {
-    for (int t = tid; t < 2 * kTabEntries * 32; t += 64 * S) tab_f[t] = tabs_g[t];
-  }
+  for (int t = tid; t < 2 * kTabEntries * 32; t += 64 * S) tab_f[t] = tabs_g[t];
   if (tid == 0) {
     mbar_init(full_bar, 1);
     mbar_init(tkey_bar, n_warps_active > 0 ? n_warps_active : 1);   // one tcgen05.commit per active warp and step
@@ -286,14 +260,7 @@ blind_rotate_fused_kernel(const c2* __restrict__ fbsk, const uint64_t* __restric
   if (active) {
     const uint32_t shp_off = (uint32_t)kGgswBytes + (uint32_t)(s * 2 + w) * 8192u;   // byte offset of this polynomial's accumulator copy
     uint32_t* shp = shadow_all + (size_t)s * 2 * kN + (size_t)w * kN;
-    double* plane = plane_all + (size_t)s * 2 * kPlaneDoubles;   // (!AL)
-    // AL: column side = this warp's own polynomial (main + overflow, lane folded in), row side = row k1 of polynomial pp
-    unsigned char* ovf_s = reinterpret_cast<unsigned char*>(plane_all) + (size_t)s * 2 * kPlaneOvfBytes + kPlaneOvfLead;
-    double* col_main = reinterpret_cast<double*>(smem + shp_off) + (tid & 31);
-    double* col_ovf = reinterpret_cast<double*>(ovf_s + (size_t)w * kPlaneOvfBytes) + (tid & 31);
-    double* row_al = nullptr;
-    double* im_col = implane_all + (size_t)(s * 2 + w) * kPlaneDoubles + (tid & 31);   // DUAL
-    double* im_row = nullptr;
+    double* plane = plane_all + (size_t)s * 2 * kPlaneDoubles;
     const int bar_id = 1 + s;
     const uint32_t tacc = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 64);
 
@@ -319,24 +286,12 @@ blind_rotate_fused_kernel(const c2* __restrict__ fbsk, const uint64_t* __restric
 
     // optional start skew between the samples of a CTA (cycles per sample index): a few hundred cycles keep every warp
     // inside the same instruction-cache window while one sample's shared-memory stores fall into another's arithmetic
-    // stagger bit 24 ("br_stagger_groups"): the skew goes to the odd samples only.  Warps 2s, 2s+1 of sample s sit on schedulers
-    // 0, 1 (s even) or 2, 3 (s odd), so every scheduler still runs ONE instruction stream (its warps in lock-step) and the SM
-    // two: the even samples' shared-memory bursts (stores, shuffles: pipes shared by the whole SM) fall into the odd samples'
-    // FP64 phases (pipes owned by a scheduler).
-    {
-      const int cyc = stagger & 0xffffff;
-      const int mult = (stagger >> 24) ? (s & 1) : s;
-      if (cyc > 0 && mult > 0) {
-        const long long t0 = clock64();
-        while (clock64() - t0 < (long long)cyc * mult) {}
-      }
+    if (stagger > 0 && s > 0) {
+      const long long t0 = clock64();
+      while (clock64() - t0 < (long long)stagger * s) {}
     }
     double xr[32], xi[32];
     const int pp = lane >> 4, k1 = 16 * w + (lane & 15);
-    if (AL)
-      row_al = plane_al_row(reinterpret_cast<double*>(smem + kGgswBytes + (size_t)(s * 2 + pp) * 8192u),
-                            reinterpret_cast<double*>(ovf_s + (size_t)pp * kPlaneOvfBytes), k1);
-    if (DUAL) im_row = implane_all + (size_t)(s * 2 + pp) * kPlaneDoubles + (size_t)k1 * kPlaneRow;
     const c2* b_own = stage + ((size_t)(pp * 2 + pp) * kHalfN + k1);
     const c2* b_in = stage + ((size_t)((1 - pp) * 2 + pp) * kHalfN + k1);
     uint32_t n_exec = 0;
@@ -360,38 +315,15 @@ blind_rotate_fused_kernel(const c2* __restrict__ fbsk, const uint64_t* __restric
       }
       // phase A + forward pass 1, interleaved
       phaseA_f1<(V & 1) != 0>(xr, xi, smem, shp_off, a & 4095u, lane);
-      if (DUAL) {
-        fwd_twiddle_col_store(xr, xi, tab_f, lane, col_main, col_ovf, im_col);
-        bar_sync(bar_id, 64);
-        row_load(xr, row_al, 0);
-        row_load(xi, im_row, 0);
-      } else {
-      if (FULLTAB) fwd_twiddle_full(xr, xi, tab_f + lane);
-      else fwd_twiddle_inplace(xr, xi, tab_f, lane);
-      // Barriers of the transposes (two warps each).  Column side: warp w touches the plane of polynomial w only; row side:
-      // thread (pp, k1) touches row k1 of the plane of polynomial pp only, in the forward and in the inverse direction.  So
-      // no barrier is needed behind the last row load (the next access to the planes is this thread's own row store) nor
-      // behind the last column load of the step (the next is this warp's own column store, or with AL its own phase C).
-      if (AL) {
-        // the plane of polynomial w overwrites the accumulator copy of polynomial w, which only this warp read (phase A above)
-        col_store_brev_al(xr, col_main, col_ovf);
-        bar_sync(bar_id, 64);
-        row_load(xr, row_al, 0);
-        bar_sync(bar_id, 64);
-        col_store_brev_al(xi, col_main, col_ovf);
-        bar_sync(bar_id, 64);
-        row_load(xi, row_al, 0);
-      } else {
-        col_store_brev(xr, plane + w * kPlaneDoubles, lane);
-        bar_sync(bar_id, 64);
-        row_load(xr, plane + pp * kPlaneDoubles, k1);
-        bar_sync(bar_id, 64);
-        col_store_brev(xi, plane + w * kPlaneDoubles, lane);
-        bar_sync(bar_id, 64);
-        row_load(xi, plane + pp * kPlaneDoubles, k1);
-      }
-      if (kRedundantBarriers) bar_sync(bar_id, 64);
-      }
+      fwd_twiddle_inplace(xr, xi, tab_f, lane);
+      col_store_brev(xr, plane + w * kPlaneDoubles, lane);
+      bar_sync(bar_id, 64);
+      row_load(xr, plane + pp * kPlaneDoubles, k1);
+      bar_sync(bar_id, 64);
+      col_store_brev(xi, plane + w * kPlaneDoubles, lane);
+      bar_sync(bar_id, 64);
+      row_load(xi, plane + pp * kPlaneDoubles, k1);
+      bar_sync(bar_id, 64);
       // forward pass 2, Fourier MAC, inverse pass 1: block by block
       fft32_fwd_s12(xr, xi);
       int nj = kLweN;
@@ -416,36 +348,16 @@ blind_rotate_fused_kernel(const c2* __restrict__ fbsk, const uint64_t* __restric
         release_stage(i);
       }
       fft32_inv_s45(xr, xi);
-      if (DUAL) {
-        inv_twiddle_row_store(xr, xi, tab_i, k1, row_al, im_row);
-        bar_sync(bar_id, 64);
-        col_load_brev_al(xr, col_main, col_ovf);
-        col_load_brev(xi, im_col, 0);
-      } else {
-      if (FULLTAB) inv_twiddle_full(xr, xi, tab_i + k1);
-      else inv_twiddle_inplace(xr, xi, tab_i, k1);
-      if (AL) {
-        row_store(xr, row_al, 0);
-        bar_sync(bar_id, 64);
-        col_load_brev_al(xr, col_main, col_ovf);
-        bar_sync(bar_id, 64);
-        row_store(xi, row_al, 0);
-        bar_sync(bar_id, 64);
-        col_load_brev_al(xi, col_main, col_ovf);
-        // the other warp is done with the plane of polynomial w (its row stores precede the barrier above): phase C below may
-        // rewrite the accumulator copy of polynomial w; the other warp's next access sits behind the next step's first barrier
-      } else {
-        row_store(xr, plane + pp * kPlaneDoubles, k1);
-        bar_sync(bar_id, 64);
+      inv_twiddle_inplace(xr, xi, tab_i, k1);
+      row_store(xr, plane + pp * kPlaneDoubles, k1);
+      bar_sync(bar_id, 64);
 
-        col_load_brev(xr, plane + w * kPlaneDoubles, lane);
-        bar_sync(bar_id, 64);
-        row_store(xi, plane + pp * kPlaneDoubles, k1);
-        bar_sync(bar_id, 64);
-        col_load_brev(xi, plane + w * kPlaneDoubles, lane);
-      }
-      if (kRedundantBarriers) bar_sync(bar_id, 64);
-      }
+      col_load_brev(xr, plane + w * kPlaneDoubles, lane);
+      bar_sync(bar_id, 64);
+      row_store(xi, plane + pp * kPlaneDoubles, k1);
+      bar_sync(bar_id, 64);
+      col_load_brev(xi, plane + w * kPlaneDoubles, lane);
+      bar_sync(bar_id, 64);
       // inverse pass 2 + phase C, interleaved
       fft32_i2_head(xr, xi);
       fin_half<0>(xr, xi, tacc, shp, lane);
@@ -472,22 +384,10 @@ blind_rotate_fused_kernel(const c2* __restrict__ fbsk, const uint64_t* __restric
   if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
 }
 
-// shared memory of blind_rotate_fused_kernel<S, V> (without the 8 KiB of alignment slack)
-static size_t fused_smem_bytes(int S, bool dual, bool fulltab = false) {
-  if (fulltab)
-    return (size_t)kGgswBytes + (size_t)S * (16384 + 2 * kPlaneOvfBytes) + 2 * 32 * 32 * sizeof(c2) + (size_t)S * 768 * sizeof(uint16_t) + 768 + 16 + 32;
-  if (dual)   // the gap in front of the block takes the small arrays when it can: worst case = a gap one byte too small for them
-    // (the caller adds 8192: block + small arrays + a gap of up to their size, 232 064 bytes at S = 4)
-    return (size_t)kGgswBytes + (size_t)S * (16384 + 2 * kPlaneOvfBytes + 2 * kPlaneDoubles * sizeof(double)) + 2 * kTabEntries * 32 * sizeof(c2) +
-           2 * ((size_t)S * 768 * sizeof(uint16_t) + 768 + 64) - 8192;
-  if (S <= 4) return br_smem_bytes(S);
-  return (size_t)kGgswBytes + (size_t)S * (16384 + 2 * kPlaneOvfBytes) + 2 * kTabEntries * 32 * sizeof(c2) + (size_t)S * 768 * sizeof(uint16_t) + 768 + 16 + 32;
-}
-
 template <int S, int V>
 static cudaError_t launch_fused_s(const c2* fbsk, const uint64_t* small, const uint64_t* luts, const uint32_t* lut_idx, uint64_t* out,
                                   const int32_t* out_rows, const c2* tabs, int count, int stagger, cudaStream_t st) {
-  const size_t smem = fused_smem_bytes(S, (V & 8) != 0, (V & 64) != 0) + 8192;   // + alignment of the block to an absolute 8 KiB boundary
+  const size_t smem = br_smem_bytes(S) + 8192;   // + alignment of the block to an absolute 8 KiB boundary
   static PerDeviceOnce once;
   bool& configured = *once.slot();
   if (!configured) {
@@ -499,37 +399,14 @@ static cudaError_t launch_fused_s(const c2* fbsk, const uint64_t* small, const u
   return cudaGetLastError();
 }
 
-// variant: bit 0 I2F digits, bit 1 tensor-memory key (4 PBS per CTA only), bit 2 keep the two redundant barriers (A/B),
-// bit 3 a transpose plane per component (4 PBS per CTA only);
-// samples: PBS per CTA, 4 or 6 (6: transpose planes inside the accumulator copies, 12 warps of 168 registers)
 cudaError_t launch_blind_rotate_fused(const c2* fbsk, const c2* fbsk_lm, const uint64_t* small, const uint64_t* luts, const uint32_t* lut_idx,
-                                      uint64_t* out, const int32_t* out_rows, const c2* tabs, int count, int variant, int stagger, int samples,
-                                      cudaStream_t st) {
+                                      uint64_t* out, const int32_t* out_rows, const c2* tabs, int count, int variant, int stagger, cudaStream_t st) {
   if (count <= 0) return cudaSuccess;
-  if (samples == 6) {
-    switch (variant & 5) {
-      case 0: return launch_fused_s<6, 0>(fbsk, small, luts, lut_idx, out, out_rows, tabs, count, stagger, st);
-      case 1: return launch_fused_s<6, 1>(fbsk, small, luts, lut_idx, out, out_rows, tabs, count, stagger, st);
-      case 4: return launch_fused_s<6, 4>(fbsk, small, luts, lut_idx, out, out_rows, tabs, count, stagger, st);
-      default: return launch_fused_s<6, 5>(fbsk, small, luts, lut_idx, out, out_rows, tabs, count, stagger, st);
-    }
-  }
-  if (variant & 8) {
-    if (variant & 1) return launch_fused_s<4, 9>(fbsk, small, luts, lut_idx, out, out_rows, tabs, count, stagger, st);
-    return launch_fused_s<4, 8>(fbsk, small, luts, lut_idx, out, out_rows, tabs, count, stagger, st);
-  }
-  if (variant & 64) {
-    if (variant & 1) return launch_fused_s<4, 65>(fbsk, small, luts, lut_idx, out, out_rows, tabs, count, stagger, st);
-    return launch_fused_s<4, 64>(fbsk, small, luts, lut_idx, out, out_rows, tabs, count, stagger, st);
-  }
-  switch (variant & 7) {
+  switch (variant & 3) {
     case 0: return launch_fused_s<4, 0>(fbsk, small, luts, lut_idx, out, out_rows, tabs, count, stagger, st);
     case 1: return launch_fused_s<4, 1>(fbsk, small, luts, lut_idx, out, out_rows, tabs, count, stagger, st);
     case 2: return launch_fused_s<4, 2>(fbsk_lm, small, luts, lut_idx, out, out_rows, tabs, count, stagger, st);
-    case 3: return launch_fused_s<4, 3>(fbsk_lm, small, luts, lut_idx, out, out_rows, tabs, count, stagger, st);
-    case 4: return launch_fused_s<4, 4>(fbsk, small, luts, lut_idx, out, out_rows, tabs, count, stagger, st);
-    case 5: return launch_fused_s<4, 5>(fbsk, small, luts, lut_idx, out, out_rows, tabs, count, stagger, st);
-    default: return cudaErrorInvalidValue;
+    default: return launch_fused_s<4, 3>(fbsk_lm, small, luts, lut_idx, out, out_rows, tabs, count, stagger, st);
   }
 }
 
@@ -540,3 +417,8 @@ cudaError_t launch_fbsk_lane_major(const c2* fbsk, c2* fbsk_lm, cudaStream_t st)
 }
 
 }  // namespace fb
+namespace fb {
+template __global__ void blind_rotate_fused_kernel<6, 1>(const c2*, const uint64_t*, const uint64_t*, const uint32_t*, uint64_t*, const int32_t*, const c2*, int, int);
+template __global__ void blind_rotate_fused_kernel<6, 0>(const c2*, const uint64_t*, const uint64_t*, const uint32_t*, uint64_t*, const int32_t*, const c2*, int, int);
+template __global__ void blind_rotate_fused_kernel<5, 1>(const c2*, const uint64_t*, const uint64_t*, const uint32_t*, uint64_t*, const int32_t*, const c2*, int, int);
+}

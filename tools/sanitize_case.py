@@ -43,6 +43,16 @@ def main():
         small = sparse_small(451)
         out = sk.bootstrap_small(small, lut[None], idx(451))
         check(small, out, (0, 3, 448, 450))
+    # the fused body's other layouts: 6 samples per CTA (ragged last CTA), one plane for both components, full twiddle tables
+    sk.set_option("br_variant", 2)
+    for samples, planes, count in ((6, 1, 6 * 148 + 5), (4, 1, 451), (4, 3, 451)):
+        sk.set_option("br_samples", samples)
+        sk.set_option("br_planes", planes)
+        small = sparse_small(count)
+        out = sk.bootstrap_small(small, lut[None], idx(count))
+        check(small, out, (0, 3, count // 2, count - 1))
+    sk.set_option("br_samples", 4)
+    sk.set_option("br_planes", 2)
     # 1-3 samples per CTA variants of the phase-by-phase body
     for count in (3, 149, 297):
         small = sparse_small(count)

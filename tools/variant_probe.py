@@ -15,6 +15,8 @@ def main():
     sizes = [int(a) for a in sys.argv[1:] if a.isdigit()] or [592, 28416]
     variants = [int(v) for v in os.environ.get("PROBE_VARIANTS", "0,1").split(",")]
     staggers = [int(v) for v in os.environ.get("PROBE_STAGGERS", "0").split(",")]
+    samples = [int(v) for v in os.environ.get("PROBE_SAMPLES", "4").split(",")]      # PBS per CTA of the fused kernel
+    barriers = [int(v) for v in os.environ.get("PROBE_BARRIERS", "0").split(",")]   # 1: keep the two unneeded barriers per step
     f = lambda x: (3 * x + 1) % 16
     lut = fb.make_lut(f)
     for B in sizes:
@@ -22,9 +24,13 @@ def main():
         cts = ck.encrypt_blocks(msgs[: min(B, 256)], seed=3)
         cts = np.ascontiguousarray(np.tile(cts, ((B + cts.shape[0] - 1) // cts.shape[0], 1))[:B])
         idx = np.zeros(B, dtype=np.uint32)
-        for v, stg in [(v, g) for v in variants for g in staggers]:
+        for v, stg, smp, brr in [(v, g, sm, bb) for v in variants for g in staggers for sm in samples for bb in barriers]:
             sk.set_option("br_variant", v)
             sk.set_option("br_stagger", stg)
+            sk.set_option("br_samples", smp)
+            sk.set_option("br_barriers", brr)
+            sk.set_option("br_stagger_groups", int(os.environ.get("PROBE_GROUPS", "0")))
+            sk.set_option("br_planes", int(os.environ.get("PROBE_PLANES", "1")))
             sk.pbs(cts, lut[None], idx)
             best = None
             for rep in range(3):
@@ -34,7 +40,7 @@ def main():
                 best = st["br_ms"] if best is None else min(best, st["br_ms"])
             pick = np.linspace(0, B - 1, num=min(B, 96), dtype=np.int64)
             ok = all(ck.decrypt_block(res[i]) == f(int(msgs[i])) for i in pick)
-            print(json.dumps({"B": B, "variant": v, "stagger": stg, "br_ms": best, "ks_ms": st["ks_ms"], "pbs_per_s": B / ((best + st["ks_ms"]) / 1e3),
+            print(json.dumps({"B": B, "variant": v, "stagger": stg, "samples": smp, "barriers": brr, "br_ms": best, "ks_ms": st["ks_ms"], "pbs_per_s": B / ((best + st["ks_ms"]) / 1e3),
                               "br_tflops": B * 194510848 / (best / 1e3) / 1e12, "ok": ok}), flush=True)
     sk.close()
 
