@@ -286,7 +286,7 @@ int fb_run_blind_rotate(fb_ctx* ctx, const uint64_t* d_small, const uint64_t* d_
     const int head = (tail > 0 && tail <= narrow_max) ? count - tail : count;
     // the fused body is built for full SMs: batches that do not fill the GPU at 4 per SM keep the phase-by-phase body
     const bool fused = ctx->br_variant >= 1 && head > 3 * ctx->sms;
-    const int fv = (ctx->br_variant - 1) | (ctx->br_barriers ? 4 : 0) | ((ctx->br_planes == 2 && S == 4 && ctx->br_variant <= 2) ? 8 : 0) | ((ctx->br_planes == 3 && S == 4 && ctx->br_variant <= 2) ? 64 : 0);
+    const int fv = (ctx->br_variant - 1) | (ctx->br_barriers ? 4 : 0) | ((ctx->br_planes == 2 && S == 4) ? 8 : 0) | ((ctx->br_planes == 3 && S == 4 && ctx->br_variant <= 2) ? 64 : 0);
     e = fused ? fb::launch_blind_rotate_fused(ctx->d_fbsk, ctx->d_fbsk_lm, d_small, d_luts, d_lut_idx, d_out, d_out_rows, ctx->d_tabs, head, fv, ctx->br_stagger | (ctx->br_stagger_groups << 24), S, ctx->stream)
               : fb::launch_blind_rotate(ctx->d_fbsk, d_small, d_luts, d_lut_idx, d_out, d_out_rows, ctx->d_tabs, head, ctx->stream);
     if (e == cudaSuccess && head < count)

@@ -514,6 +514,10 @@ cudaError_t launch_blind_rotate_fused(const c2* fbsk, const c2* fbsk_lm, const u
       default: return launch_fused_s<6, 5>(fbsk, small, luts, lut_idx, out, out_rows, tabs, count, stagger, st);
     }
   }
+  if ((variant & 10) == 10) {   // plane per component + tensor-memory key
+    if (variant & 1) return launch_fused_s<4, 11>(fbsk_lm, small, luts, lut_idx, out, out_rows, tabs, count, stagger, st);
+    return launch_fused_s<4, 10>(fbsk_lm, small, luts, lut_idx, out, out_rows, tabs, count, stagger, st);
+  }
   if (variant & 8) {
     if (variant & 1) return launch_fused_s<4, 9>(fbsk, small, luts, lut_idx, out, out_rows, tabs, count, stagger, st);
     return launch_fused_s<4, 8>(fbsk, small, luts, lut_idx, out, out_rows, tabs, count, stagger, st);

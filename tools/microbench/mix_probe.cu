@@ -2,6 +2,7 @@
 // 148 CTAs x 256 threads (2 warps per scheduler, like the throughput blind rotation), small loop body (instruction-cache resident).
 // Per iteration and warp: ND DFMA (constant-bank multiplier) interleaved with the "other" instructions of the mode.
 //   cycles per iteration if the two kinds overlap = max(FP64 pipe time, other pipe time); if they serialise = the sum.
+// (loads next to FP64 work: lds_cost_probe.cu; instruction classes: coissue_probe.cu)
 // nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o mix_probe mix_probe.cu
 #include <cstdio>
 #include <cstdint>
@@ -83,17 +84,10 @@ int main() {
   run<6, 0>("8 STS.64 alone");
   run<2, 16>("DFMA + 2 STS.128 (LSU alone ~74)");
   run<2, 0>("2 STS.128 alone");
-  run<3, 16>("DFMA + 4 LDS.128 (LSU alone ~64)");
-  run<3, 0>("4 LDS.128 alone");
   run<4, 16>("DFMA + 8 SHFL (alone 64)");
   run<4, 0>("8 SHFL alone");
-  run<5, 16>("DFMA + 16 IADD");
-  run<5, 0>("16 IADD alone");
   run<8, 16>("DFMA + 16 x (LOP3, IADD)");
   run<8, 0>("16 x (LOP3, IADD) alone");
   run<8, 8>("8 DFMA + 16 x (LOP3, IADD)");
-  run<7, 16>("DFMA + 8 x (LOP3, LDS.32, IADD, AND)");
-  run<7, 0>("8 x (LOP3, LDS.32, IADD, AND) alone");
-  run<7, 8>("8 DFMA + 8 x (LOP3, LDS.32, IADD, AND)");
   return 0;
 }
