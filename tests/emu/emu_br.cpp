@@ -284,3 +284,87 @@ extern "C" void emu_negacyclic_mul(const int64_t* a_int, const uint64_t* b_torus
   memcpy(out, sa.acc.data(), sizeof(uint64_t) * kN);
 }
 
+
+// ---- round 2, last session: the transposes through the other plane layouts ------------------------------------------
+// One sample's worth of registers goes through the forward twiddle + transpose and the inverse twiddle + transpose in
+//   layout 0: one contiguous plane for both components, one after the other (col_store_brev / row_load / row_store / col_load_brev)
+//   layout 1: planes inside the 8 KiB accumulator copies + overflow blocks (col_store_brev_al / plane_al_row / col_load_brev_al)
+//   layout 2: a plane per component with the twiddles fused into the stores (fwd_twiddle_col_store / inv_twiddle_row_store)
+//   layout 3: layout 1 with the full twiddle tables (fb_full_twiddle / fwd_twiddle_full / inv_twiddle_full)
+// returns the number of registers that differ from layout 0 bit for bit (0 expected), or -1 if a layout wrote outside its blocks
+extern "C" int emu_plane_layouts_check(int layout, unsigned seed) {
+  tabs();
+  static Regs ref[2][32], got[2][32], in[2][32];
+  srand(seed);
+  for (int w = 0; w < 2; w++)
+    for (int lane = 0; lane < 32; lane++)
+      for (int r = 0; r < 32; r++) {
+        in[w][lane].xr[r] = (double)(rand() % 2000001 - 1000000) / 7.0;
+        in[w][lane].xi[r] = (double)(rand() % 2000001 - 1000000) / 11.0;
+      }
+  auto run = [&](int L, Regs (&R)[2][32]) -> bool {
+    memcpy(R, in, sizeof(in));
+    // shared memory of one sample: two accumulator copies of 8 KiB, two overflow blocks, two imaginary planes, guard words between
+    const size_t kGuard = 16;
+    std::vector<double> shadow(2 * 1024 + kGuard, -7.0), ovf(2 * (kPlaneOvfBytes / 8) + kGuard, -7.0), implane(2 * kPlaneDoubles + kGuard, -7.0),
+        plane(2 * kPlaneDoubles + kGuard, -7.0);
+    std::vector<c2> full_f(1024), full_i(1024);
+    for (int t = 0; t < 1024; t++) {
+      full_f[t] = fb_full_twiddle(g_tab_f, t >> 5, t & 31);
+      full_i[t] = fb_full_twiddle(g_tab_i, t >> 5, t & 31);
+    }
+    auto main_of = [&](int p) { return shadow.data() + p * 1024; };
+    auto ovf_of = [&](int p) { return ovf.data() + p * (kPlaneOvfBytes / 8) + kPlaneOvfLead / 8; };
+    auto pass = [&](bool inverse) {
+      for (int comp = 0; comp < 2; comp++) {   // layouts 0, 1, 3: the components one after the other
+        if (L == 2 && comp == 1) break;
+        for (int w = 0; w < 2; w++)
+          for (int lane = 0; lane < 32; lane++) {
+            Regs& T = R[w][lane];
+            const int pp = lane >> 4, k1 = 16 * w + (lane & 15);
+            double (&x)[32] = comp ? T.xi : T.xr;
+            if (!inverse) {
+              if (comp == 0 && L != 2) { if (L == 3) fwd_twiddle_full(T.xr, T.xi, full_f.data() + lane); else fwd_twiddle_inplace(T.xr, T.xi, g_tab_f, lane); }
+              if (L == 0) col_store_brev(x, plane.data() + w * kPlaneDoubles, lane);
+              else if (L == 2) fwd_twiddle_col_store(T.xr, T.xi, g_tab_f, lane, main_of(w) + lane, ovf_of(w) + lane, implane.data() + w * kPlaneDoubles + lane);
+              else col_store_brev_al(x, main_of(w) + lane, ovf_of(w) + lane);
+            } else {
+              if (comp == 0 && L != 2) { if (L == 3) inv_twiddle_full(T.xr, T.xi, full_i.data() + k1); else inv_twiddle_inplace(T.xr, T.xi, g_tab_i, k1); }
+              if (L == 0) row_store(x, plane.data() + pp * kPlaneDoubles, k1);
+              else if (L == 2) inv_twiddle_row_store(T.xr, T.xi, g_tab_i, k1, plane_al_row(main_of(pp), ovf_of(pp), k1), implane.data() + pp * kPlaneDoubles + k1 * kPlaneRow);
+              else row_store(x, plane_al_row(main_of(pp), ovf_of(pp), k1), 0);
+            }
+          }
+        for (int cc = comp; cc < (L == 2 ? 2 : comp + 1); cc++)   // barrier; the readers
+          for (int w = 0; w < 2; w++)
+            for (int lane = 0; lane < 32; lane++) {
+              Regs& T = R[w][lane];
+              const int pp = lane >> 4, k1 = 16 * w + (lane & 15);
+              double (&x)[32] = cc ? T.xi : T.xr;
+              if (!inverse) {
+                if (L == 0) row_load(x, plane.data() + pp * kPlaneDoubles, k1);
+                else if (L == 2 && cc == 1) row_load(x, implane.data() + pp * kPlaneDoubles + k1 * kPlaneRow, 0);
+                else row_load(x, plane_al_row(main_of(pp), ovf_of(pp), k1), 0);
+              } else {
+                if (L == 0) col_load_brev(x, plane.data() + w * kPlaneDoubles, lane);
+                else if (L == 2 && cc == 1) col_load_brev(x, implane.data() + w * kPlaneDoubles + lane, 0);
+                else col_load_brev_al(x, main_of(w) + lane, ovf_of(w) + lane);
+              }
+            }
+      }
+    };
+    pass(false);
+    pass(true);
+    bool clean = true;
+    for (size_t g = 0; g < kGuard; g++)
+      clean = clean && shadow[2 * 1024 + g] == -7.0 && ovf[2 * (kPlaneOvfBytes / 8) + g] == -7.0 && implane[2 * kPlaneDoubles + g] == -7.0 && plane[2 * kPlaneDoubles + g] == -7.0;
+    // the aliased planes stay inside their blocks: rows 0..29 end at double 30*34 = 1020 <= 1024, the overflow rows at (96 + 2*272) / 8 = 80
+    return clean;
+  };
+  if (!run(0, ref) || !run(layout, got)) return -1;
+  int bad = 0;
+  for (int w = 0; w < 2; w++)
+    for (int lane = 0; lane < 32; lane++)
+      bad += memcmp(&ref[w][lane], &got[w][lane], sizeof(Regs)) != 0;
+  return bad;
+}

@@ -234,3 +234,12 @@ def test_duo_trivial_input_is_exact(emu_duo, emu_fbsk, server_key):
     emu_duo.emu_duo_blind_rotate(_p(emu_fbsk), _p(small), _p(lut), _p(acc), -1)
     ref = tfhe.bootstrap_small(server_key, small, lut)
     assert (tfhe.sample_extract(acc) == ref).all()
+
+
+@pytest.mark.parametrize("layout", [1, 2, 3])
+def test_emulated_plane_layouts_are_bit_identical(emu, layout):
+    """round 2: the transposes of the fused throughput kernel through (1) planes inside the accumulator copies + overflow
+    blocks, (2) a plane per component with the twiddles fused into the stores, (3) layout 1 with the full twiddle tables --
+    every register bit-identical to the contiguous split planes, and nothing written outside the blocks"""
+    for seed in (1, 2, 3, 4):
+        assert emu.emu_plane_layouts_check(layout, seed) == 0
