@@ -61,6 +61,8 @@ int main() {
   run<16, 0, 16>();
   run<16, 4, 16>(); run<8, 8, 16>(); run<4, 16, 16>();
   run<16, 8, 16>(); run<8, 16, 16>();
+  // below the shared-memory bound (loads hidden under the FP64 pipe if they cost the scheduler nothing)
+  run<16, 1, 16>(); run<16, 2, 16>(); run<8, 2, 16>(); run<8, 4, 16>(); run<4, 4, 16>(); run<4, 8, 16>();
   run<16, 4, 0>(); run<8, 8, 0>(); run<4, 16, 0>(); run<16, 8, 0>();
   return 0;
 }
