@@ -279,8 +279,23 @@ int fb_run_blind_rotate(fb_ctx* ctx, const uint64_t* d_small, const uint64_t* d_
   if (count <= narrow_max) {
     e = narrow(d_small, d_lut_idx, d_out, d_out_rows, count);
   } else {
-    // 6 PBS per CTA (fused body only, option "br_samples") once the batch is wider than a wave of 4 per SM
-    const int S = (ctx->br_samples == 6 && ctx->br_variant >= 1 && count > 4 * ctx->sms) ? 6 : fb::br_samples_per_cta();
+    // PBS per CTA of the throughput launch (fused body only, option "br_samples"): 4, 6, or 0 = whichever the wave arithmetic
+    // favours.  Measured wave times on a B200 (ms): 4 per SM 6.24, 6 per SM 9.47, latency kernel 2.30 (up to one PBS per SM),
+    // pair kernel 4.30 (up to two per SM); per PBS 6 per SM is 1 % slower, so it only wins through the quantisation, e.g.
+    // 1 020 = 888 + 132: 11.8 ms against two waves of 592 = 12.5.
+    auto est = [&](int Sx) {
+      const int qx = ctx->sms * Sx;
+      const double tw = Sx == 6 ? 9.47 : 6.24;
+      const int full = count / qx, rem = count % qx;
+      if (rem == 0) return full * tw;
+      if (full > 0 && rem <= narrow_max) return full * tw + (rem <= ctx->sms ? 2.30 : 4.30);
+      return (full + 1) * tw;
+    };
+    int S = fb::br_samples_per_cta();
+    if (ctx->br_variant >= 1 && count > 4 * ctx->sms) {
+      if (ctx->br_samples == 6) S = 6;
+      else if (ctx->br_samples == 0 && est(6) < 0.97 * est(4)) S = 6;
+    }
     const int q = ctx->sms * S;
     const int tail = (q > 0) ? count % q : 0;
     const int head = (tail > 0 && tail <= narrow_max) ? count - tail : count;
@@ -356,7 +371,7 @@ const OptionDesc kOptions[] = {
     {"wide_pair", 0, 2},                    // latency kernel with two PBS per CTA: 0 never, 1 for batches between one and two waves of SMs, 2 for every narrow batch
     {"wide_pair_prefetch", 0, 2},           // pair kernel: GGSW groups fetched before the pre-MAC barrier
     {"wide_pair_offset", 0, 100000},        // pair kernel: cycles the second sample of a CTA starts late
-    {"br_samples", 4, 6},                   // fused throughput kernel: PBS per CTA, 4 or 6 (6: transpose planes inside the accumulator copies)
+    {"br_samples", 0, 6},                   // fused throughput kernel: PBS per CTA, 4 or 6 (6: transpose planes inside the accumulator copies), 0 = by wave arithmetic
     {"br_stagger_groups", 0, 1},            // 1: "br_stagger" delays the odd samples of a CTA only (two scheduler groups, one instruction stream per scheduler)
     {"br_planes", 1, 3},                    // fused throughput kernel at 4 PBS per CTA: 2 = a transpose plane per component (one barrier per transpose)
     {"br_barriers", 0, 1},                  // fused throughput kernel: 1 keeps the two per-step barriers that are not needed (A/B measurements)
@@ -420,9 +435,9 @@ extern "C" int fb_set_option(fb_ctx* ctx, const char* name, int64_t value) {
     case 10: ctx->wide_pair_prefetch = (int)value; break;
     case 11: ctx->wide_pair_offset = (int)value; break;
     case 12:
-      if (value == 5) return fb_fail(ctx, FB_ERR_ARG, "br_samples is 4 or 6");
+      if (value != 0 && value != 4 && value != 6) return fb_fail(ctx, FB_ERR_ARG, "br_samples is 0 (automatic), 4 or 6");
       ctx->br_samples = (int)value;
-      ctx->quantum = ctx->sms * ctx->br_samples;
+      ctx->quantum = ctx->sms * (value == 6 ? 6 : 4);
       break;
     case 13: ctx->br_stagger_groups = (int)value; break;
     case 14: ctx->br_planes = (int)value; break;

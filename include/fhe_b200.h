@@ -65,9 +65,18 @@ int fb_sync(fb_ctx* ctx);
 /* Every knob is per context and set explicitly; the library reads nothing from the environment.
  *   "latency_threshold"      batches up to this many PBS run the one-PBS-per-CTA blind rotation (default 296, 0 = never)
  *   "cluster_threshold"      batches up to this many PBS run the one-PBS-per-SM-pair blind rotation (default 0 = never)
- *   "br_variant"             throughput blind rotation at 4 PBS per SM: 0 phase-by-phase body, 1 fused body (default), 2 fused body
- *                            with the digits through the integer-to-double unit, 3 / 4 = 1 / 2 with the Fourier key in tensor memory
+ *   "br_variant"             throughput blind rotation: 0 phase-by-phase body, 1 fused body, 2 fused body with the digits through
+ *                            the integer-to-double unit (default), 3 / 4 = 1 / 2 with the Fourier key in tensor memory
+ *   "br_planes"              fused body at 4 PBS per CTA, transposes: 1 both components through one plane one after the other,
+ *                            2 a plane per component -- the real one inside the accumulator copy (default; one barrier per
+ *                            transpose), 3 = 1 with the planes inside the accumulator copies and both full inter-pass twiddle
+ *                            tables in shared memory (built once per launch).  Bit-identical outputs.
+ *   "br_samples"             fused body: PBS per CTA, 4 (default) or 6 (transpose planes inside the accumulator copies, 12 warps of
+ *                            168 registers, 888 PBS per wave on a B200; used for batches wider than 4 per SM).  fb_pbs_batch_quantum
+ *                            follows.  Bit-identical outputs.
  *   "br_stagger"             fused throughput kernel: start skew between the samples of a CTA, cycles per sample index (default 0)
+ *   "br_stagger_groups"      1: the skew goes to the odd samples only (two scheduler groups, one instruction stream per scheduler)
+ *   "br_barriers"            1: keep the two per-step barriers round 2 found unnecessary (A/B measurements only)
  *   "ks_variant"             keyswitch GEMM: 0 mma.sync, 1 tcgen05.mma kind::i8 with TMA operands and TMEM accumulators (default 1)
  *   "wide_skew", "wide_prefetch"   tuning of the latency kernel (defaults 200 cycles, 3 groups)
  *   "wide_pair"              two PBS per CTA (twiddles in tensor memory): 1 for batches between one and two waves of SMs
