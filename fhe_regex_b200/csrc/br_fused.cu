@@ -15,6 +15,11 @@
 //     block between them;
 //   * inverse pass 2 + phase C: the untwist is folded into the last-stage butterflies as a pending rotation, its real
 //     factor into the FMAs of a three-instruction torus rounding (br_core.cuh::torus32_round_scaled).
+// Shared-memory layouts of the transposes (template bits of V; all bit-identical):
+//   one plane for both components, one after the other (V & 72 == 0, 4 PBS per CTA);
+//   planes inside the accumulator copies (S > 4: 6 PBS per CTA; br_core.cuh "planes aliased");
+//   a plane per component, the real one inside the accumulator copy (V & 8, the default: one barrier per transpose);
+//   planes inside the accumulator copies + full inter-pass twiddle tables built once per launch (V & 64).
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "br_core.cuh"
@@ -360,37 +365,38 @@ blind_rotate_fused_kernel(const c2* __restrict__ fbsk, const uint64_t* __restric
       }
       // phase A + forward pass 1, interleaved
       phaseA_f1<(V & 1) != 0>(xr, xi, smem, shp_off, a & 4095u, lane);
+      // Transposes (barriers of two warps).  Column side: warp w touches the plane(s) of polynomial w only; row side: thread
+      // (pp, k1) touches row k1 of the plane(s) of polynomial pp only, in the forward and in the inverse direction.  So no
+      // barrier is needed behind the last row load (the next access to the planes is this thread's own row store) nor behind
+      // the last column load of the step (the next is this warp's own column store -- or, with the plane inside the
+      // accumulator copy, its own phase C; the other warp's next access sits behind the next step's first barrier).
       if (DUAL) {
         fwd_twiddle_col_store(xr, xi, tab_f, lane, col_main, col_ovf, im_col);
         bar_sync(bar_id, 64);
         row_load(xr, row_al, 0);
         row_load(xi, im_row, 0);
       } else {
-      if (FULLTAB) fwd_twiddle_full(xr, xi, tab_f + lane);
-      else fwd_twiddle_inplace(xr, xi, tab_f, lane);
-      // Barriers of the transposes (two warps each).  Column side: warp w touches the plane of polynomial w only; row side:
-      // thread (pp, k1) touches row k1 of the plane of polynomial pp only, in the forward and in the inverse direction.  So
-      // no barrier is needed behind the last row load (the next access to the planes is this thread's own row store) nor
-      // behind the last column load of the step (the next is this warp's own column store, or with AL its own phase C).
-      if (AL) {
-        // the plane of polynomial w overwrites the accumulator copy of polynomial w, which only this warp read (phase A above)
-        col_store_brev_al(xr, col_main, col_ovf);
-        bar_sync(bar_id, 64);
-        row_load(xr, row_al, 0);
-        bar_sync(bar_id, 64);
-        col_store_brev_al(xi, col_main, col_ovf);
-        bar_sync(bar_id, 64);
-        row_load(xi, row_al, 0);
-      } else {
-        col_store_brev(xr, plane + w * kPlaneDoubles, lane);
-        bar_sync(bar_id, 64);
-        row_load(xr, plane + pp * kPlaneDoubles, k1);
-        bar_sync(bar_id, 64);
-        col_store_brev(xi, plane + w * kPlaneDoubles, lane);
-        bar_sync(bar_id, 64);
-        row_load(xi, plane + pp * kPlaneDoubles, k1);
-      }
-      if (kRedundantBarriers) bar_sync(bar_id, 64);
+        if (FULLTAB) fwd_twiddle_full(xr, xi, tab_f + lane);
+        else fwd_twiddle_inplace(xr, xi, tab_f, lane);
+        if (AL) {
+          // the plane of polynomial w overwrites the accumulator copy of polynomial w, which only this warp read (phase A above)
+          col_store_brev_al(xr, col_main, col_ovf);
+          bar_sync(bar_id, 64);
+          row_load(xr, row_al, 0);
+          bar_sync(bar_id, 64);
+          col_store_brev_al(xi, col_main, col_ovf);
+          bar_sync(bar_id, 64);
+          row_load(xi, row_al, 0);
+        } else {
+          col_store_brev(xr, plane + w * kPlaneDoubles, lane);
+          bar_sync(bar_id, 64);
+          row_load(xr, plane + pp * kPlaneDoubles, k1);
+          bar_sync(bar_id, 64);
+          col_store_brev(xi, plane + w * kPlaneDoubles, lane);
+          bar_sync(bar_id, 64);
+          row_load(xi, plane + pp * kPlaneDoubles, k1);
+        }
+        if (kRedundantBarriers) bar_sync(bar_id, 64);
       }
       // forward pass 2, Fourier MAC, inverse pass 1: block by block
       fft32_fwd_s12(xr, xi);
@@ -422,29 +428,26 @@ blind_rotate_fused_kernel(const c2* __restrict__ fbsk, const uint64_t* __restric
         col_load_brev_al(xr, col_main, col_ovf);
         col_load_brev(xi, im_col, 0);
       } else {
-      if (FULLTAB) inv_twiddle_full(xr, xi, tab_i + k1);
-      else inv_twiddle_inplace(xr, xi, tab_i, k1);
-      if (AL) {
-        row_store(xr, row_al, 0);
-        bar_sync(bar_id, 64);
-        col_load_brev_al(xr, col_main, col_ovf);
-        bar_sync(bar_id, 64);
-        row_store(xi, row_al, 0);
-        bar_sync(bar_id, 64);
-        col_load_brev_al(xi, col_main, col_ovf);
-        // the other warp is done with the plane of polynomial w (its row stores precede the barrier above): phase C below may
-        // rewrite the accumulator copy of polynomial w; the other warp's next access sits behind the next step's first barrier
-      } else {
-        row_store(xr, plane + pp * kPlaneDoubles, k1);
-        bar_sync(bar_id, 64);
-
-        col_load_brev(xr, plane + w * kPlaneDoubles, lane);
-        bar_sync(bar_id, 64);
-        row_store(xi, plane + pp * kPlaneDoubles, k1);
-        bar_sync(bar_id, 64);
-        col_load_brev(xi, plane + w * kPlaneDoubles, lane);
-      }
-      if (kRedundantBarriers) bar_sync(bar_id, 64);
+        if (FULLTAB) inv_twiddle_full(xr, xi, tab_i + k1);
+        else inv_twiddle_inplace(xr, xi, tab_i, k1);
+        if (AL) {
+          row_store(xr, row_al, 0);
+          bar_sync(bar_id, 64);
+          col_load_brev_al(xr, col_main, col_ovf);
+          bar_sync(bar_id, 64);
+          row_store(xi, row_al, 0);
+          bar_sync(bar_id, 64);
+          col_load_brev_al(xi, col_main, col_ovf);
+        } else {
+          row_store(xr, plane + pp * kPlaneDoubles, k1);
+          bar_sync(bar_id, 64);
+          col_load_brev(xr, plane + w * kPlaneDoubles, lane);
+          bar_sync(bar_id, 64);
+          row_store(xi, plane + pp * kPlaneDoubles, k1);
+          bar_sync(bar_id, 64);
+          col_load_brev(xi, plane + w * kPlaneDoubles, lane);
+        }
+        if (kRedundantBarriers) bar_sync(bar_id, 64);
       }
       // inverse pass 2 + phase C, interleaved
       fft32_i2_head(xr, xi);
