@@ -33,9 +33,25 @@ constexpr int kKB = kK / UM_BK;                  // 80 k-blocks
 constexpr uint32_t kABytes = UM_BM * UM_BK, kBBytes = UM_BN * UM_BK, kStageBytes = kABytes + kBBytes;   // 16 K + 32 K
 constexpr size_t kUmmaSmem = (size_t)UM_STAGES * kStageBytes + 1024 /* alignment slack */ + 256 /* barriers */;
 
-__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_dst),
-               "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+// L2 eviction policy of a TMA load.  The key byte planes (61 MB) are re-read by every wave of tiles; the digit matrix (10 KB per
+// ciphertext, 291 MB at 28 416) is read by the 24 CTAs that share a row tile and is dead afterwards.  Measured at 28 416 ciphertexts
+// (ncu dram__bytes_read): no hints 1.89 GB, key evict_last + digits evict_normal 1.73 GB (kept), digits evict_first 2.43 GB (the
+// 24 readers of a digit tile are not in step: an early eviction costs a re-read) against 0.35 GB compulsory; the launch takes 1.22 ms
+// in every case (tensor pipe / L2 bound, 1.5 TB/s of DRAM is not its limit).  The rest of the over-read is the key being streamed
+// through both L2 halves once per wave of tiles; a banded tile order (37 row tiles x 4 key tiles per wave) would bring it to ~0.66 GB.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_normal() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(smem_dst),
+               "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy)
                : "memory");
 }
 // whole-warp-free single-thread wait (the producer and the MMA issuer are single threads)
@@ -126,6 +142,7 @@ ks_umma_kernel(const __grid_constant__ CUtensorMap tm_dig, const __grid_constant
   if (warp == 0) {
     // ---- producer ------------------------------------------------------------------------------------------------------
     if (lane == 0) {
+      const uint64_t pol_dig = l2_policy_evict_normal(), pol_key = l2_policy_evict_last();
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int mt = tile / kNT, nt = tile % kNT;
@@ -134,8 +151,8 @@ ks_umma_kernel(const __grid_constant__ CUtensorMap tm_dig, const __grid_constant
           mbar_wait_thread(empty + s, ph ^ 1u);
           mbar_arrive_expect_tx(full + s, kStageBytes);
           const uint32_t dstA = base + s * kStageBytes, dstB = dstA + kABytes;
-          tma_load_2d(dstA, &tm_dig, kb * UM_BK, mt * UM_BM, full + s);
-          tma_load_2d(dstB, &tm_key, kb * UM_BK, nt * UM_BN, full + s);
+          tma_load_2d(dstA, &tm_dig, kb * UM_BK, mt * UM_BM, full + s, pol_dig);
+          tma_load_2d(dstB, &tm_key, kb * UM_BK, nt * UM_BN, full + s, pol_key);
         }
       }
     }
