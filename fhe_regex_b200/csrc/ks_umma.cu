@@ -34,11 +34,10 @@ constexpr uint32_t kABytes = UM_BM * UM_BK, kBBytes = UM_BN * UM_BK, kStageBytes
 constexpr size_t kUmmaSmem = (size_t)UM_STAGES * kStageBytes + 1024 /* alignment slack */ + 256 /* barriers */;
 
 // L2 eviction policy of a TMA load.  The key byte planes (61 MB) are re-read by every wave of tiles; the digit matrix (10 KB per
-// ciphertext, 291 MB at 28 416) is read by the 24 CTAs that share a row tile and is dead afterwards.  Measured at 28 416 ciphertexts
-// (ncu dram__bytes_read): no hints 1.89 GB, key evict_last + digits evict_normal 1.73 GB (kept), digits evict_first 2.43 GB (the
-// 24 readers of a digit tile are not in step: an early eviction costs a re-read) against 0.35 GB compulsory; the launch takes 1.22 ms
-// in every case (tensor pipe / L2 bound, 1.5 TB/s of DRAM is not its limit).  The rest of the over-read is the key being streamed
-// through both L2 halves once per wave of tiles; a banded tile order (37 row tiles x 4 key tiles per wave) would bring it to ~0.66 GB.
+// ciphertext, 291 MB at 28 416) is read by the CTAs that share a row tile and is dead afterwards.  Measured at 28 416 ciphertexts
+// (ncu dram__bytes_read per launch, 0.35 GB compulsory): row-major tile order without hints 1.89 GB; key evict_last + digits
+// evict_normal 1.73 GB (kept); digits evict_first 2.43 GB (the readers of a digit tile are not in step: an early eviction costs a
+// re-read); with the banded tile order below 0.80 GB and 1.22 -> 1.11 ms (profiles/r02_traffic_bench_batch.csv).
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
   uint64_t p;
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
@@ -102,6 +101,21 @@ __device__ __forceinline__ void tmem_ld32x(uint32_t taddr, uint32_t (&v)[32]) {
                : "memory");
 }
 
+// Tile order.  Output tiles are walked in bands of kBandRows row tiles; inside a band the key column tiles go in groups of
+// kBandCols, the row tile next, the column of the group fastest.  A wave of 148 concurrent tiles then works on ~37 digit tiles
+// (48 MB, re-used by the 6 groups of the band from L2) and 4 key tiles (10 MB) instead of 6 digit tiles and the whole 61 MB key:
+// the key is streamed once per band (6 times at 28 416 ciphertexts) instead of once per wave (36 times).
+constexpr int kBandRows = 37, kBandCols = 4;
+static_assert(kNT % kBandCols == 0, "key column tiles come in whole groups");
+__device__ __forceinline__ void tile_coords(int tile, int m_tiles, int& mt, int& nt) {
+  const int band = tile / (kBandRows * kNT);
+  const int rows = min(kBandRows, m_tiles - band * kBandRows);          // the last band may be short
+  const int u = tile - band * (kBandRows * kNT);
+  const int g = u / (rows * kBandCols), v = u - g * (rows * kBandCols);
+  mt = band * kBandRows + v / kBandCols;
+  nt = g * kBandCols + v % kBandCols;
+}
+
 __global__ void __launch_bounds__(192, 1)
 ks_umma_kernel(const __grid_constant__ CUtensorMap tm_dig, const __grid_constant__ CUtensorMap tm_key, const uint64_t* __restrict__ in,
                const int32_t* __restrict__ in_rows, uint64_t* __restrict__ out, int count, int m_tiles) {
@@ -145,7 +159,8 @@ ks_umma_kernel(const __grid_constant__ CUtensorMap tm_dig, const __grid_constant
       const uint64_t pol_dig = l2_policy_evict_normal(), pol_key = l2_policy_evict_last();
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int mt = tile / kNT, nt = tile % kNT;
+        int mt, nt;
+        tile_coords(tile, m_tiles, mt, nt);
         for (int kb = 0; kb < kKB; kb++, it++) {
           const uint32_t s = it % UM_STAGES, ph = (it / UM_STAGES) & 1u;
           mbar_wait_thread(empty + s, ph ^ 1u);
@@ -182,7 +197,8 @@ ks_umma_kernel(const __grid_constant__ CUtensorMap tm_dig, const __grid_constant
     const int quarter = warp & 3;               // TMEM lanes 32 * quarter .. + 31 = rows of the tile
     uint32_t t_local = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, t_local++) {
-      const int mt = tile / kNT, nt = tile % kNT;
+      int mt, nt;
+      tile_coords(tile, m_tiles, mt, nt);
       const uint32_t a = t_local & 1u, aph = (t_local >> 1) & 1u;
       mbar_wait(acc_full + a, aph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
