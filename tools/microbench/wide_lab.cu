@@ -26,6 +26,8 @@ __device__ __forceinline__ void half_sync(int P) { asm volatile("bar.sync %0, 12
 // MODE bit 0: half 1 idles through the per-half stages (what does a lone half cost?)
 //      bit 1: no stores in the transform stages (stores replaced by a cheap dependency sink)
 //      bit 2: no FP64 butterflies (loads and stores only)
+//      bit 3: the GGSW values of the MAC come from registers (no shared-memory key reads: upper bound of what serving the key
+//             from tensor memory could gain)
 template <int MODE>
 __global__ void __launch_bounds__(256, 1)
 lab_kernel(const c2* __restrict__ fbsk, const uint16_t* __restrict__ at_g, const c2* __restrict__ wtab, uint32_t* __restrict__ out,
@@ -86,11 +88,25 @@ lab_kernel(const c2* __restrict__ fbsk, const uint16_t* __restrict__ at_g, const
     if (!idle) wide::fwd_stage3(bufB_p, bufA_p, t);
     mbar_wait(full_bar + (n & 1), (uint32_t)(n >> 1) & 1u);
     const c2* ggsw = reinterpret_cast<const c2*>(smem + (size_t)(n & 1) * kStageBytes);
-    c2 gpre[12];
-    wide::mac_prefetch<3>(ggsw, P, t, gpre);
+    c2 gpre[16];
+    if (MODE & 8) {
+#pragma unroll
+      for (int g = 0; g < 16; g++) { gpre[g].x = __hiloint2double(0x3fe00000 + g, (int)(a + n)); gpre[g].y = __hiloint2double(0x3fd00000 + g, (int)a); }
+    } else {
+      c2 g3[12];
+      wide::mac_prefetch<3>(ggsw, P, t, g3);
+#pragma unroll
+      for (int g = 0; g < 12; g++) gpre[g] = g3[g];
+    }
     __syncthreads();
     STAMP(3)
-    wide::mac_inv_stage1<3>(bufA, bufA + kHalfN, ggsw, gpre, P, t, tw, bufB_p);
+    if (MODE & 8) wide::mac_inv_stage1<4>(bufA, bufA + kHalfN, ggsw, gpre, P, t, tw, bufB_p);
+    else {
+      c2 g3[12];
+#pragma unroll
+      for (int g = 0; g < 12; g++) g3[g] = gpre[g];
+      wide::mac_inv_stage1<3>(bufA, bufA + kHalfN, ggsw, g3, P, t, tw, bufB_p);
+    }
     __syncthreads();
     STAMP(4)
     if (P == 1 && skew_cycles > 0) {
@@ -165,5 +181,7 @@ int main() {
   run<0>("product stages", fbsk, at, wtab, out, stamps, 450, false);
   run<0>("product stages", fbsk, at, wtab, out, stamps, 700, false);
   run<1>("half 1 idles through the per-half stages", fbsk, at, wtab, out, stamps, 0, true);
+  run<8>("GGSW values from registers (no key reads)", fbsk, at, wtab, out, stamps, 200, true);
+  run<8>("GGSW values from registers (no key reads)", fbsk, at, wtab, out, stamps, 0, false);
   return 0;
 }
