@@ -123,6 +123,9 @@ def lib():
     L.fb_kernel_timing_enable.argtypes = [vp, C.c_int]
     L.fb_measure_fp64_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
     L.fb_pbs_batch_quantum.argtypes = [vp]
+    L.fb_host_alloc.argtypes = [sz, C.POINTER(vp)]
+    L.fb_host_free.argtypes = [vp]
+    L.fb_host_free.restype = None
     L.fb_client_key_from_bincode.argtypes = [vp, sz, vp, vp]
     L.fb_client_keygen_server.argtypes = [vp, vp, C.c_uint64, vp, vp]
     L.fb_client_encrypt_str.argtypes = [vp, vp, sz, C.c_uint64, vp]
@@ -315,12 +318,26 @@ class ClientKey:
         return int(lib().fb_client_decrypt_radix(_p(self.big), _p(np.ascontiguousarray(radix_ct))))
 
 
+def pinned_empty(shape, dtype=np.uint64) -> np.ndarray:
+    """numpy array over a page-locked buffer of the library (fb_host_alloc): uploads from it run at PCIe speed.  Falls back to
+    an ordinary array when no device is present (this is host memory only -- the compute entry points never fall back)."""
+    import weakref
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+    ptr = C.c_void_p()
+    if n == 0 or lib().fb_host_alloc(n, C.byref(ptr)) != FB_OK or not ptr.value:
+        return np.empty(shape, dtype=dtype)
+    buf = (C.c_ubyte * n).from_address(ptr.value)
+    weakref.finalize(buf, lib().fb_host_free, ptr.value)   # the array (and its views) keep buf alive through .base
+    return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+
 def encrypt_str(client_key: ClientKey, s: str, seed: int = 1) -> np.ndarray:
     """encrypt_str (ciphertext.rs:32-40): [len, 4, 2049] u64; ValueError on non-ASCII."""
     b = s.encode("latin-1", errors="replace") if s.isascii() else None
     if b is None:
         raise ValueError("content contains non-ascii characters")
-    out = np.empty((len(b), 4, BIG), dtype=np.uint64)
+    out = pinned_empty((len(b), 4, BIG), np.uint64)   # what a host hands to has_match: page-locked when a device is there
     raw = np.frombuffer(b, dtype=np.uint8) if len(b) else np.zeros(0, dtype=np.uint8)
     rc = lib().fb_client_encrypt_str(_p(client_key.big), _p(np.ascontiguousarray(raw)), len(b), seed, _p(out))
     if rc != FB_OK:

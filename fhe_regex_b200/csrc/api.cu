@@ -325,6 +325,21 @@ int fb_run_lincomb(fb_ctx* ctx, uint64_t* d_arena, const int32_t* out_rows, cons
   return FB_OK;
 }
 
+extern "C" int fb_host_alloc(size_t bytes, void** out) {
+  if (!out) return FB_ERR_ARG;
+  *out = nullptr;
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();   // not sticky: the caller falls back to pageable memory
+    return FB_ERR_CUDA;
+  }
+  *out = p;
+  return FB_OK;
+}
+extern "C" void fb_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
 extern "C" int fb_kernel_timing_enable(fb_ctx* ctx, int on) {
   if (!ctx) return FB_ERR_ARG;
   ctx->timing = on != 0;

@@ -252,6 +252,15 @@ int fb_set_cluster_threshold(fb_ctx* ctx, int max_count);
 /* PBS batch sizes that fill the GPU evenly are multiples of this (SM count x samples per CTA) */
 int fb_pbs_batch_quantum(fb_ctx* ctx);
 
+/* ---- page-locked host buffers ------------------------------------------------------------------- */
+/* Every entry point takes plain caller-owned host pointers (the reference hands `&[RadixCiphertext]` to has_match,
+ * engine.rs:8-12, out of the `Vec` encrypt_str built, ciphertext.rs:32-40).  A buffer obtained here is page-locked: its
+ * uploads run at PCIe speed and truly asynchronously (a 64-character content is 4.2 MB, a 256-character one 16.8 MB --
+ * 0.3 / 1.2 ms from pageable memory against 0.1 / 0.4 ms from page-locked memory).  Optional: pageable buffers work everywhere.
+ * fb_host_alloc returns FB_ERR_CUDA when no device is present. */
+int fb_host_alloc(size_t bytes, void** out);
+void fb_host_free(void* p);
+
 /* ---- tfhe-rs 0.2.0 wire formats (host only; layouts in fhe_regex_b200/csrc/wire.cpp) ---------------------------- */
 /* integer::ServerKey <-> (keyswitch key container, Fourier bootstrapping key in serialized order) */
 size_t fb_server_key_bincode_size(void);

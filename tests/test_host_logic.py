@@ -7,6 +7,7 @@ import random
 import re
 import subprocess
 
+import numpy as np
 import pytest
 
 import fhe_regex_b200 as fb
@@ -201,3 +202,16 @@ def test_product_does_not_touch_the_oracle():
                 if name.endswith((".py", ".cu", ".cpp", ".cuh", ".h")):
                     txt = open(os.path.join(dirpath, name)).read()
                     assert "from oracle" not in txt and "import oracle" not in txt and "libtfhe_oracle" not in txt and "oracle/" not in txt, name
+
+
+def test_pinned_empty_is_an_ordinary_array_without_a_device():
+    """fb_host_alloc / pinned_empty: page-locked when a device is present, a plain numpy array otherwise -- the same
+    shape, dtype and contiguity either way, and encrypt_str (which allocates through it) still round-trips"""
+    a = fb.pinned_empty((5, 4, fb.BIG), np.uint64)
+    assert a.shape == (5, 4, fb.BIG) and a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"]
+    a[:] = 7
+    assert int(a.sum()) == 7 * a.size
+    assert fb.pinned_empty((0, 4, fb.BIG)).shape == (0, 4, fb.BIG)
+    ck = fb.ClientKey.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "client_key"))
+    ct = fb.encrypt_str(ck, "a+b", seed=5)
+    assert ct.shape == (3, 4, fb.BIG) and [ck.decrypt(c) for c in ct] == [ord(ch) for ch in "a+b"]
