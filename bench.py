@@ -43,7 +43,7 @@ if ROOT not in sys.path:
 FLOP_PER_PBS = 742 * 262144            # 4 transforms x (5*1024*10 + 6*1024) + 4*1024*8 per CMUX
 # DRAM bytes of one blind_rotate_fused launch at the default batch, from the ncu pass recorded in
 # profiles/r02_traffic_bench_batch.csv (dram__bytes_read.sum + dram__bytes_write.sum, B = 28 416)
-BR_TRAFFIC_MEASURED = {28416: 313040896 + 456266496}
+BR_TRAFFIC_MEASURED = {28416: 317583360 + 456988160}
 BSK_BYTES = 742 * 4 * 1024 * 16
 KS_MAC_PER_PBS = 2048 * 5 * 743
 KS_BYTES_PER_LAUNCH_KEY = 2048 * 5 * 743 * 8
@@ -431,7 +431,9 @@ def main():
                         else [c256, c256[:-3] + "abc"])
             base = [fb.encrypt_str(ck, t_, seed=20 + i) for i, t_ in enumerate(distinct)]
             texts = [distinct[i % len(distinct)] for i in range(m)]
-            cts = np.stack([base[i % len(distinct)] for i in range(m)])
+            cts = fb.pinned_empty((m,) + base[0].shape, np.uint64)      # what a serving host stages its documents in (fb_host_alloc)
+            for i in range(m):
+                cts[i] = base[i % len(distinct)]
             fb.has_match_many(sk, cts, pattern)
             barrier()
             tm = time.perf_counter()
