@@ -389,6 +389,7 @@ const OptionDesc kOptions[] = {
     {"br_samples", 0, 6},                   // fused throughput kernel: PBS per CTA, 4 or 6 (6: transpose planes inside the accumulator copies), 0 = by wave arithmetic
     {"br_stagger_groups", 0, 1},            // 1: "br_stagger" delays the odd samples of a CTA only (two scheduler groups, one instruction stream per scheduler)
     {"br_planes", 1, 3},                    // fused throughput kernel at 4 PBS per CTA: 2 = a transpose plane per component (one barrier per transpose)
+    {"pbs_chunks", 3, 5},                   // fb_pbs_batch: 3 = chunks of 4, rest, 4 waves (default), 5 = 1, 6, rest, 6, 1 for batches of at least 24 waves
     {"br_barriers", 0, 1},                  // fused throughput kernel: 1 keeps the two per-step barriers that are not needed (A/B measurements)
     {"dist_shard_min", 0, 1 << 30},         // fb_has_match_dist: levels of at most this many PBS are computed by every rank instead of being sharded (default: the SM count)
 };
@@ -412,8 +413,9 @@ int64_t* option_slot(fb_ctx* ctx, const char* name, int64_t& shadow, int& which)
         case 12: shadow = ctx->br_samples; break;
         case 13: shadow = ctx->br_stagger_groups; break;
         case 14: shadow = ctx->br_planes; break;
-        case 15: shadow = ctx->br_barriers; break;
-        case 16: shadow = ctx->dist_shard_min; break;
+        case 15: shadow = ctx->pbs_chunks; break;
+        case 16: shadow = ctx->br_barriers; break;
+        case 17: shadow = ctx->dist_shard_min; break;
       }
       return &shadow;
     }
@@ -456,8 +458,9 @@ extern "C" int fb_set_option(fb_ctx* ctx, const char* name, int64_t value) {
       break;
     case 13: ctx->br_stagger_groups = (int)value; break;
     case 14: ctx->br_planes = (int)value; break;
-    case 15: ctx->br_barriers = (int)value; break;
-    case 16: ctx->dist_shard_min = (int)value; break;
+    case 15: ctx->pbs_chunks = (int)value; break;
+    case 16: ctx->br_barriers = (int)value; break;
+    case 17: ctx->dist_shard_min = (int)value; break;
   }
   return FB_OK;
 }
@@ -527,15 +530,23 @@ extern "C" int fb_pbs_batch(fb_ctx* ctx, const uint64_t* h_in, const uint64_t* h
   uint64_t* d_in = (uint64_t*)ctx->in.p;
   uint64_t* d_out = (uint64_t*)ctx->out.p;
   const uint32_t* d_idx = (const uint32_t*)ctx->lut_idx.p;
-  // Large batches are pipelined in at most three chunks of whole throughput waves: the upload of chunk k+1 and the
-  // download of chunk k-1 run on their own streams (two DMA engines) under the bootstraps of chunk k, so only the
-  // first upload and the last download are exposed -- hence a short first and a short last chunk (4 waves each)
-  // around one long one.  Few chunks: every extra launch ends in a tail where SMs wait for the slowest CTA
-  // (measured: 12 chunks of 4 waves cost more than the copies they hide).
+  // Large batches are pipelined in chunks of whole throughput waves: the upload of chunk k+1 and the download of chunk k-1
+  // run on their own streams (two DMA engines) under the bootstraps of chunk k, so only the first upload and the last
+  // download are exposed -- hence a short first and a short last chunk (4 waves each) around one long one.  Few chunks: every
+  // extra launch ends in a tail where SMs wait for the slowest CTA (measured: 12 chunks of 4 waves cost more than the copies
+  // they hide; option "pbs_chunks" 5 = chunks of 1, 6, rest, 6, 1 waves: 0.6 ms exposed instead of 1.6 ms, but +2.5 ms of
+  // launch tails at 28 416 PBS -- tools/e2e_gap_probe.py).
   const size_t q = (size_t)ctx->quantum;
-  size_t bounds[4] = {0, count, count, count};
+  size_t bounds[6] = {0, count, count, count, count, count};
   size_t n_chunks = 1;
-  if (count >= 16 * q) {
+  if (count >= 24 * q && ctx->pbs_chunks >= 5) {
+    const size_t mid = (count - 14 * q) / q * q;
+    bounds[1] = q;
+    bounds[2] = 7 * q;
+    bounds[3] = 7 * q + mid;
+    bounds[4] = count - q;
+    n_chunks = 5;
+  } else if (count >= 16 * q) {
     const size_t mid = (count - 8 * q) / q * q;
     bounds[1] = 4 * q;
     bounds[2] = 4 * q + mid;
@@ -553,7 +564,7 @@ extern "C" int fb_pbs_batch(fb_ctx* ctx, const uint64_t* h_in, const uint64_t* h
   }
   if (!ctx->h2d_stream) FB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
   if (!ctx->d2h_stream) FB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
-  while (ctx->pipe_events.size() < 2 * n_chunks + 1) {
+  while (ctx->pipe_events.size() < 3 * n_chunks + 1) {   // per chunk: uploaded, bootstrapped, "next upload may go"; + start
     cudaEvent_t e;
     FB_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     ctx->pipe_events.push_back(e);
@@ -564,28 +575,71 @@ extern "C" int fb_pbs_batch(fb_ctx* ctx, const uint64_t* h_in, const uint64_t* h
   FB_CUDA(ctx, cudaEventRecord(start, ctx->stream));
   FB_CUDA(ctx, cudaStreamWaitEvent(ctx->h2d_stream, start, 0));
   FB_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h_stream, start, 0));
-  for (size_t k = 0; k < n_chunks; k++) {
+  // option "plan_timing": the timeline of the pipeline on stderr (when each upload, each chunk's bootstraps and each download
+  // ended, in ms from the start of the call on the device)
+  const bool trace = ctx->plan_timing;
+  std::vector<cudaEvent_t> tev;
+  auto mark = [&](cudaStream_t st) {
+    if (!trace) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) == cudaSuccess) { cudaEventRecord(e, st); tev.push_back(e); }
+  };
+  mark(ctx->stream);
+  // The upload of chunk k+1 is released by an event on the compute stream placed between the keyswitch and the blind rotation
+  // of chunk k, not queued up front: with all uploads in flight from the start of the call the first kernels did not begin
+  // before the LAST upload had ended (measured with the timeline below: the first chunk finished 8.5 ms late, exactly the
+  // 466 MB / 55 GB/s of the whole input), which was the whole gap between this call and the device-resident one.
+  auto upload = [&](size_t k) -> cudaError_t {
     const size_t off = bounds[k], n = bounds[k + 1] - bounds[k];
-    FB_CUDA(ctx, cudaMemcpyAsync(d_in + off * FB_LWE_BIG_WORDS, h_in + off * FB_LWE_BIG_WORDS, n * FB_LWE_BIG_WORDS * 8,
-                                 cudaMemcpyHostToDevice, ctx->h2d_stream));
-    FB_CUDA(ctx, cudaEventRecord(ctx->pipe_events[2 * k], ctx->h2d_stream));
-  }
+    cudaError_t e = cudaMemcpyAsync(d_in + off * FB_LWE_BIG_WORDS, h_in + off * FB_LWE_BIG_WORDS, n * FB_LWE_BIG_WORDS * 8, cudaMemcpyHostToDevice,
+                                    ctx->h2d_stream);
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->pipe_events[2 * k], ctx->h2d_stream);
+    mark(ctx->h2d_stream);
+    return e;
+  };
+  FB_CUDA(ctx, upload(0));
   for (size_t k = 0; k < n_chunks; k++) {
     const size_t off = bounds[k], n = bounds[k + 1] - bounds[k];
     FB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->pipe_events[2 * k], 0));
-    if ((rc = fb_pbs_batch_dev(ctx, d_in + off * FB_LWE_BIG_WORDS, (const uint64_t*)ctx->luts.p, d_idx + off, n, d_out + off * FB_LWE_BIG_WORDS))) {
+    rc = fb_reserve(ctx, ctx->small, n * FB_LWE_SMALL_WORDS * 8);
+    if (!rc) rc = fb_run_keyswitch(ctx, d_in + off * FB_LWE_BIG_WORDS, nullptr, (uint64_t*)ctx->small.p, (int)n);
+    if (!rc && k + 1 < n_chunks) {
+      cudaEvent_t go = ctx->pipe_events[2 * n_chunks + 1 + k];
+      cudaError_t e = cudaEventRecord(go, ctx->stream);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->h2d_stream, go, 0);
+      if (e == cudaSuccess) e = upload(k + 1);
+      if (e != cudaSuccess) rc = fb_cuda_fail(ctx, e, "fb_pbs_batch upload");
+    }
+    if (!rc)
+      rc = fb_run_blind_rotate(ctx, (const uint64_t*)ctx->small.p, (const uint64_t*)ctx->luts.p, d_idx + off, d_out + off * FB_LWE_BIG_WORDS, nullptr, (int)n);
+    if (rc) {
       cudaStreamSynchronize(ctx->h2d_stream);   // nothing of this call may still touch the caller's buffers
       cudaStreamSynchronize(ctx->d2h_stream);
       cudaStreamSynchronize(ctx->stream);
+      for (cudaEvent_t e : tev) cudaEventDestroy(e);
       return rc;
     }
     FB_CUDA(ctx, cudaEventRecord(ctx->pipe_events[2 * k + 1], ctx->stream));
+    mark(ctx->stream);
     FB_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h_stream, ctx->pipe_events[2 * k + 1], 0));
     FB_CUDA(ctx, cudaMemcpyAsync(h_out + off * FB_LWE_BIG_WORDS, d_out + off * FB_LWE_BIG_WORDS, n * FB_LWE_BIG_WORDS * 8,
                                  cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    mark(ctx->d2h_stream);
   }
   FB_CUDA(ctx, cudaStreamSynchronize(ctx->d2h_stream));
   FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (trace && tev.size() == 1 + 3 * n_chunks) {
+    // marks in queue order: start, upload 0, then per chunk k: [upload k+1,] bootstraps k, download k
+    auto at = [&](size_t i) { float ms = 0.f; cudaEventElapsedTime(&ms, tev[0], tev[i]); return ms; };
+    std::fprintf(stderr, "fb_pbs_batch %zu PBS in %zu chunks:", count, n_chunks);
+    for (size_t k = 0; k < n_chunks; k++) {
+      const size_t up = k == 0 ? 1 : 3 * k - 1, br = k + 1 < n_chunks ? 3 * k + 3 : 3 * k + 2;
+      std::fprintf(stderr, "  [%zu: %zu PBS, upload done %.2f, bootstraps done %.2f, download done %.2f]", k, bounds[k + 1] - bounds[k], at(up), at(br),
+                   at(br + 1));
+    }
+    std::fprintf(stderr, " ms\n");
+  }
+  for (cudaEvent_t e : tev) cudaEventDestroy(e);
   return FB_OK;
 }
 

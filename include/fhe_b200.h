@@ -76,6 +76,9 @@ int fb_sync(fb_ctx* ctx);
  *                            follows.  Bit-identical outputs.
  *   "br_stagger"             fused throughput kernel: start skew between the samples of a CTA, cycles per sample index (default 0)
  *   "br_stagger_groups"      1: the skew goes to the odd samples only (two scheduler groups, one instruction stream per scheduler)
+ *   "pbs_chunks"             fb_pbs_batch pipelines large batches in chunks of whole waves: 3 = 4, rest, 4 waves (default), 5 = 1, 6,
+ *                            rest, 6, 1 waves for batches of at least 24 waves (less copy exposed, more launch tails: measured slower)
+ *   "plan_timing"            also prints the timeline of every pipelined fb_pbs_batch call
  *   "br_barriers"            1: keep the two per-step barriers round 2 found unnecessary (A/B measurements only)
  *   "ks_variant"             keyswitch GEMM: 0 mma.sync, 1 tcgen05.mma kind::i8 with TMA operands and TMEM accumulators (default 1)
  *   "wide_skew", "wide_prefetch"   tuning of the latency kernel (defaults 200 cycles, 3 groups)

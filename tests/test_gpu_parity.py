@@ -207,10 +207,10 @@ def test_blind_rotation_variants_agree(client_key, gpu_key):
         assert np.abs(tfhe.torus_err(tfhe.phase_batch(client_key.big, outs[name]), ph_t)).max() < 2 * PBS_ERR_MAX, name
 
 
-@pytest.mark.parametrize("quanta,extra", [(8, 1), (11, 300), (20, 37)])
+@pytest.mark.parametrize("quanta,extra", [(8, 1), (11, 300), (20, 37), (24, 0), (25, 311)])
 def test_pbs_batch_pipelined_chunks(quanta, extra, fck, gpu_key):
-    """fb_pbs_batch splits batches beyond 8 throughput quanta into two or three chunks whose copies overlap the
-    bootstraps: every chunk, both sides of every possible chunk boundary and the ragged tail must come back right"""
+    """fb_pbs_batch splits batches beyond 8 throughput quanta into two, three or (from 24 quanta on) five chunks whose copies
+    overlap the bootstraps: every chunk, both sides of every possible chunk boundary and the ragged tail must come back right"""
     q = gpu_key.pbs_quantum()
     count = quanta * q + extra
     base_msgs = (np.arange(128) * 5 + 1) % 16
@@ -220,7 +220,11 @@ def test_pbs_batch_pipelined_chunks(quanta, extra, fck, gpu_key):
     fs = [lambda x: (x + 9) % 16, lambda x: int(x < 4), lambda x: (3 * x) % 16]
     luts = np.stack([fb.make_lut(f) for f in fs])
     idx = (np.arange(count) % 3).astype(np.uint32)
-    out = gpu_key.pbs(cts, luts, idx)
+    prev = gpu_key.set_option("pbs_chunks", 5 if quanta >= 24 else 3)
+    try:
+        out = gpu_key.pbs(cts, luts, idx)
+    finally:
+        gpu_key.set_option("pbs_chunks", prev)
     pick = {0, 1, count - 1, count - 2, count // 2} | set(range(0, count, 997))
     for b in range(q, count, q):                       # chunk boundaries are multiples of the quantum
         pick |= {b - 1, b, min(b + 1, count - 1)}
