@@ -297,12 +297,23 @@ def main():
     # ---- host-buffer (e2e) leg ---------------------------------------------------------------------
     for _ in range(2):
         step_host()
+    sampler_h = ClockSampler(local_rank)
+    if rank == 0:
+        sampler_h.start()
+        time.sleep(0.3)
+    sk.timing(True)
+    sk.kernel_stats(reset=True)
     barrier()
+    th0 = time.time()
     te = time.perf_counter()
     for _ in range(args.steps):
         step_host()
     barrier()
     e2e_s = time.perf_counter() - te
+    th1 = time.time()
+    kst_h = sk.kernel_stats(reset=True)      # the same kernels, timed inside the host-buffer calls
+    sk.timing(False)
+    clocks_h = sampler_h.stop(th0, th1) if rank == 0 else None
     # correctness of what the host-buffer leg produced: decrypt the same sample of ITS outputs
     h_np = h_out.numpy().view(np.uint64)
     for i in chk:
@@ -354,7 +365,8 @@ def main():
                                        "algorithmic_gbs": ks_bytes / (ks_ms * 1e-3) / 1e9, "hbm_peak_gbs": hbm_peak,
                                        "hbm_peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * BIG * 8 + luts_np.nbytes + idx_np.nbytes, "d2h_bytes_per_step": B * BIG * 8,
-                    "ms_per_step": e2e_ms / args.steps, "api": "fb_pbs_batch (host buffers, pinned)"},
+                    "ms_per_step": e2e_ms / args.steps, "api": "fb_pbs_batch (host buffers, pinned)",
+                    "kernel_ms_per_step": (kst_h["br_ms"] + kst_h["ks_ms"]) / args.steps, "clocks": clocks_h},
             # kernels of this repository launched inside the timed region: per step ks_decompose + ks_gemm + blind_rotate
             "gpu_launches": int(2 * kst["ks_launches"] + kst["br_launches"] + kst["lin_launches"]),
             "clocks": clocks,

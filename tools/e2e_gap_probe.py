@@ -16,14 +16,18 @@ def main():
     base = ck.encrypt_blocks(np.arange(256) % 16, seed=3)
     h_in = fb.pinned_empty((B, fb.BIG)); h_out = fb.pinned_empty((B, fb.BIG))
     h_in[:] = np.tile(base, (B // 256, 1))
-    lut = np.ascontiguousarray(fb.make_lut(lambda x: (3 * x + 1) % 16)[None])
-    idx = np.zeros(B, dtype=np.uint32)
+    n_luts = int(os.environ.get("PROBE_LUTS", "1"))        # bench.py uses 36 accumulators and uniform indices
+    lut = np.ascontiguousarray(np.stack([fb.make_lut(lambda x, k=k: (3 * x + 1 + (0 if os.environ.get("PROBE_SAME") else k)) % 16) for k in range(n_luts)]))
+    idx = np.random.default_rng(7).integers(0, n_luts, size=B).astype(np.uint32)
+    if os.environ.get("PROBE_SORTED"):
+        idx = np.sort(idx)
     L = fb.lib()
     p = lambda a: a.ctypes.data_as(C.c_void_p)
     def call():
-        rc = L.fb_pbs_batch(sk._h, p(h_in), p(lut), 1, p(idx), B, p(h_out)); assert rc == 0
+        rc = L.fb_pbs_batch(sk._h, p(h_in), p(lut), n_luts, p(idx), B, p(h_out)); assert rc == 0
     sk.timing(True)
-    for chunks in (3, 5):
+    sk.set_option("br_sync", int(os.environ.get("PROBE_SYNC", "1")))
+    for chunks in (3,):
         sk.set_option("pbs_chunks", chunks)
         call(); call()
         sk.kernel_stats(reset=True)
@@ -34,7 +38,19 @@ def main():
         sk.set_option("plan_timing", 1); call(); sk.set_option("plan_timing", 0)   # timeline of one call on stderr
         print(json.dumps({"pbs_chunks": chunks, "wall_ms_per_call": wall, "br_ms_per_call": st["br_ms"] / 3, "ks_ms_per_call": st["ks_ms"] / 3,
                           "br_launches_per_call": st["br_launches"] / 3, "outside_kernels_ms": wall - (st["br_ms"] + st["ks_ms"]) / 3}), flush=True)
-    assert ck.decrypt_block(h_out[5]) == (3 * 5 + 1) % 16
+    # the same batch device-resident (fb_pbs_batch_dev on torch tensors), same accumulators and indices
+    try:
+        import torch
+        d_in = torch.from_numpy(h_in.view(np.int64).copy()).cuda(); d_out = torch.empty_like(d_in)
+        d_l = torch.from_numpy(lut.view(np.int64)).cuda(); d_i = torch.from_numpy(idx.view(np.int32)).cuda()
+        for _ in range(2): sk.pbs_dev(d_in.data_ptr(), d_l.data_ptr(), d_i.data_ptr(), B, d_out.data_ptr())
+        sk.sync(); sk.kernel_stats(reset=True)
+        for _ in range(3): sk.pbs_dev(d_in.data_ptr(), d_l.data_ptr(), d_i.data_ptr(), B, d_out.data_ptr())
+        sk.sync(); st = sk.kernel_stats(reset=True)
+        print(json.dumps({"device_resident": True, "br_ms_per_call": st["br_ms"] / 3, "ks_ms_per_call": st["ks_ms"] / 3}), flush=True)
+    except ImportError:
+        pass
+    assert ck.decrypt_block(h_out[5]) == (3 * 5 + 1 + (0 if os.environ.get("PROBE_SAME") else int(idx[5]))) % 16
     sk.close()
 
 if __name__ == "__main__":
