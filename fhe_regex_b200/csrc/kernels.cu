@@ -178,6 +178,9 @@ blind_rotate_kernel(const c2* __restrict__ fbsk, const uint64_t* __restrict__ sm
       tmem_wait_st();
     }
     __syncwarp();
+    // the samples of the CTA start their rotation together (their accumulator reads above have different latencies, and
+    // samples that start apart stay apart: br_fused.cu, "br_sync")
+    if (S > 1) bar_sync(15, 32 * (int)n_warps_active);
 
     double xr[32], xi[32];
     const int pp = lane >> 4, k1 = 16 * w + (lane & 15);
