@@ -302,7 +302,7 @@ int fb_run_blind_rotate(fb_ctx* ctx, const uint64_t* d_small, const uint64_t* d_
     // the fused body is built for full SMs: batches that do not fill the GPU at 4 per SM keep the phase-by-phase body
     const bool fused = ctx->br_variant >= 1 && head > 3 * ctx->sms;
     const int fv = (ctx->br_variant - 1) | (ctx->br_barriers ? 4 : 0) | ((ctx->br_planes == 2 && S == 4) ? 8 : 0) | ((ctx->br_planes == 3 && S == 4 && ctx->br_variant <= 2) ? 64 : 0);
-    e = fused ? fb::launch_blind_rotate_fused(ctx->d_fbsk, ctx->d_fbsk_lm, d_small, d_luts, d_lut_idx, d_out, d_out_rows, ctx->d_tabs, head, fv, ctx->br_stagger | (ctx->br_stagger_groups << 24) | (ctx->br_sync << 25), S, ctx->stream)
+    e = fused ? fb::launch_blind_rotate_fused(ctx->d_fbsk, ctx->d_fbsk_lm, d_small, d_luts, d_lut_idx, d_out, d_out_rows, ctx->d_tabs, head, fv, ctx->br_stagger | (ctx->br_stagger_groups << 24) | (ctx->br_sync << 25) | (ctx->br_resync << 26), S, ctx->stream)
               : fb::launch_blind_rotate(ctx->d_fbsk, d_small, d_luts, d_lut_idx, d_out, d_out_rows, ctx->d_tabs, head, ctx->stream);
     if (e == cudaSuccess && head < count)
       e = narrow(d_small + (size_t)head * FB_LWE_SMALL_WORDS, d_lut_idx + head, d_out_rows ? d_out : d_out + (size_t)head * FB_LWE_BIG_WORDS,
@@ -390,7 +390,8 @@ const OptionDesc kOptions[] = {
     {"br_stagger_groups", 0, 1},            // 1: "br_stagger" delays the odd samples of a CTA only (two scheduler groups, one instruction stream per scheduler)
     {"br_planes", 1, 3},                    // fused throughput kernel at 4 PBS per CTA: 2 = a transpose plane per component (one barrier per transpose)
     {"pbs_chunks", 3, 5},                   // fb_pbs_batch: 3 = chunks of 4, rest, 4 waves (default), 5 = 1, 6, rest, 6, 1 for batches of at least 24 waves
-    {"br_sync", 0, 2},                      // fused throughput kernel: 1 = the samples of a CTA start their rotation together (default), 2 = and meet again at every CMUX step, 0 = neither
+    {"br_sync", 0, 1},                      // fused throughput kernel: 1 = the samples of a CTA start their rotation together (default)
+    {"br_resync", 0, 63},                   // fused throughput kernel: the samples of a CTA meet at a barrier every this many CMUX steps (0 = never)
     {"br_barriers", 0, 1},                  // fused throughput kernel: 1 keeps the two per-step barriers that are not needed (A/B measurements)
     {"dist_shard_min", 0, 1 << 30},         // fb_has_match_dist: levels of at most this many PBS are computed by every rank instead of being sharded (default: the SM count)
 };
@@ -416,8 +417,9 @@ int64_t* option_slot(fb_ctx* ctx, const char* name, int64_t& shadow, int& which)
         case 14: shadow = ctx->br_planes; break;
         case 15: shadow = ctx->pbs_chunks; break;
         case 16: shadow = ctx->br_sync; break;
-        case 17: shadow = ctx->br_barriers; break;
-        case 18: shadow = ctx->dist_shard_min; break;
+        case 17: shadow = ctx->br_resync; break;
+        case 18: shadow = ctx->br_barriers; break;
+        case 19: shadow = ctx->dist_shard_min; break;
       }
       return &shadow;
     }
@@ -462,8 +464,9 @@ extern "C" int fb_set_option(fb_ctx* ctx, const char* name, int64_t value) {
     case 14: ctx->br_planes = (int)value; break;
     case 15: ctx->pbs_chunks = (int)value; break;
     case 16: ctx->br_sync = (int)value; break;
-    case 17: ctx->br_barriers = (int)value; break;
-    case 18: ctx->dist_shard_min = (int)value; break;
+    case 17: ctx->br_resync = (int)value; break;
+    case 18: ctx->br_barriers = (int)value; break;
+    case 19: ctx->dist_shard_min = (int)value; break;
   }
   return FB_OK;
 }

@@ -321,12 +321,16 @@ blind_rotate_fused_kernel(const c2* __restrict__ fbsk, const uint64_t* __restric
       tmem_wait_st();
     }
     __syncwarp();
-    // Every sample of the CTA starts its rotation together (stagger bits 25-26, "br_sync" >= 1): the warps that own a body
-    // polynomial have just read their accumulator from global memory, each with its own latency -- with 36 accumulators in
-    // random order the samples of a CTA left the initialisation up to a few thousand cycles apart, nothing brings them back
-    // into step afterwards, and lock-step is worth 2-3 % (profiles/r02_experiments.md section 11).
-    const int sync_mode = (stagger >> 25) & 3;
-    if (sync_mode >= 1) bar_sync(15, 32 * (int)n_warps_active);
+    // Every sample of the CTA starts its rotation together (stagger bit 25, "br_sync" 1): the warps that own a body polynomial
+    // have just read their accumulator from global memory, each with its own latency -- with 36 accumulators in random order
+    // the samples of a CTA left the initialisation up to a few thousand cycles apart -- and they meet again every
+    // `resync` CMUX steps (stagger bits 26-31, "br_resync"): nothing else brings samples that drift apart back into step, and
+    // lock-step is worth several per cent (profiles/r02_experiments.md section 11); a barrier at EVERY step costs more than it
+    // gains (the slowest warp of each step sets the pace).
+    const bool sync_start = ((stagger >> 25) & 1) != 0;
+    const uint32_t resync = ((uint32_t)stagger >> 26) & 63u;
+    uint32_t resync_cnt = 0;
+    if (sync_start) bar_sync(15, 32 * (int)n_warps_active);
 
     // optional start skew between the samples of a CTA (cycles per sample index): a few hundred cycles keep every warp
     // inside the same instruction-cache window while one sample's shared-memory stores fall into another's arithmetic
@@ -355,7 +359,10 @@ blind_rotate_fused_kernel(const c2* __restrict__ fbsk, const uint64_t* __restric
       if (!__any_sync(0xffffffffu, need[i] != 0)) continue;
       const uint32_t a = at[i];
       const uint32_t par = n_exec & 1u;
-      if (sync_mode >= 2) bar_sync(15, 32 * (int)n_warps_active);   // (measurement only) back into step at every CMUX
+      if (resync != 0 && ++resync_cnt == resync) {
+        resync_cnt = 0;
+        bar_sync(15, 32 * (int)n_warps_active);
+      }
       if (kTKey) stage_key_to_tmem(n_exec);   // this step's key: shared-memory stage -> tensor memory (needed ~7k cycles from here)
       n_exec++;
       if (!__any_sync(0xffffffffu, (a & 0x8000u) != 0)) {   // this sample skips the step but takes part in the hand-over

@@ -56,7 +56,8 @@ struct fb_ctx {
   int br_stagger_groups = 0;   // 1: the skew goes to the odd samples only (option "br_stagger_groups")
   int br_planes = 2;           // 2: a transpose plane per component in the fused kernel at 4 PBS per CTA (option "br_planes")
   int pbs_chunks = 3;          // fb_pbs_batch: 3 = chunks of 4, rest, 4 waves; 5 = 1, 6, rest, 6, 1 for batches of at least 24 waves (option "pbs_chunks")
-  int br_sync = 1;             // fused throughput kernel: 1 = the samples of a CTA start their rotation together, 2 = and meet at every step (option "br_sync")
+  int br_sync = 1;             // fused throughput kernel: 1 = the samples of a CTA start their rotation together (option "br_sync")
+  int br_resync = 8;           // ... and meet at a CTA-wide barrier every this many CMUX steps, 0 = never (option "br_resync")
   int br_barriers = 0;         // fused throughput kernel: 1 keeps two unneeded barriers per step (option "br_barriers", A/B only)
   int br_stagger = 0;          // fused throughput kernel: start skew between the samples of a CTA, cycles per sample index (option "br_stagger")
   bool plan_absorb = true;     // false: reference-shaped plan (option "plan_reference_shaped" = 1)

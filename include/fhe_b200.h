@@ -81,8 +81,9 @@ int fb_sync(fb_ctx* ctx);
  *   "plan_timing"            also prints the timeline of every pipelined fb_pbs_batch call
  *   "br_sync"                fused body: 1 = the samples of a CTA start their rotation together, behind one CTA-wide barrier after
  *                            the accumulators are read (default: their read latencies differ, and samples that leave the
- *                            initialisation apart stay apart: 2-3 % with 36 accumulators in random order), 2 = and meet again at
- *                            every CMUX step (measured slower), 0 = neither (round-2 behaviour before the last session)
+ *                            initialisation apart stay apart: 2-3 % with 36 accumulators in random order), 0 = not
+ *   "br_resync"              fused body: the samples of a CTA meet at a CTA-wide barrier every this many CMUX steps (default 8:
+ *                            -5 % against never; 1 = every step is slower than never; 0 = never).  Bit-identical outputs.
  *   "br_barriers"            1: keep the two per-step barriers round 2 found unnecessary (A/B measurements only)
  *   "ks_variant"             keyswitch GEMM: 0 mma.sync, 1 tcgen05.mma kind::i8 with TMA operands and TMEM accumulators (default 1)
  *   "wide_skew", "wide_prefetch"   tuning of the latency kernel (defaults 200 cycles, 3 groups)

@@ -613,14 +613,14 @@ def test_throughput_blind_rotation_layouts_bit_identical(client_key, gpu_key, fc
     f = lambda x: (7 * x + 2) % 16
     lut = fb.make_lut(f)
     idx = np.zeros(n, dtype=np.uint32)
-    names = ("br_variant", "br_samples", "br_planes", "br_barriers", "br_stagger", "br_stagger_groups", "br_sync")
+    names = ("br_variant", "br_samples", "br_planes", "br_barriers", "br_stagger", "br_stagger_groups", "br_sync", "br_resync")
     saved = [gpu_key.get_option(k) for k in names]
     prev_lat = gpu_key.set_latency_threshold(0)
     try:
         outs = {}
-        for cfg in ((1, 4, 1, 0, 0, 0, 1), (1, 4, 1, 1, 0, 0, 1), (1, 4, 2, 0, 0, 0, 1), (1, 4, 3, 0, 0, 0, 1), (1, 6, 1, 0, 0, 0, 1), (1, 6, 1, 0, 3000, 1, 1),
-                    (2, 4, 1, 0, 0, 0, 1), (2, 4, 2, 0, 0, 0, 1), (2, 4, 3, 0, 0, 0, 1), (2, 6, 1, 0, 0, 0, 1), (2, 4, 2, 0, 0, 0, 0), (2, 4, 2, 0, 0, 0, 2),
-                    (2, 6, 1, 0, 0, 0, 2)):
+        for cfg in ((1, 4, 1, 0, 0, 0, 1, 0), (1, 4, 1, 1, 0, 0, 1, 8), (1, 4, 2, 0, 0, 0, 1, 8), (1, 4, 3, 0, 0, 0, 1, 8), (1, 6, 1, 0, 0, 0, 1, 8),
+                    (1, 6, 1, 0, 3000, 1, 1, 0), (2, 4, 1, 0, 0, 0, 1, 0), (2, 4, 2, 0, 0, 0, 1, 8), (2, 4, 3, 0, 0, 0, 1, 8), (2, 6, 1, 0, 0, 0, 1, 8),
+                    (2, 4, 2, 0, 0, 0, 0, 0), (2, 4, 2, 0, 0, 0, 1, 1), (2, 6, 1, 0, 0, 0, 1, 3), (2, 4, 2, 0, 0, 0, 0, 63)):
             for k, v in zip(names, cfg):
                 gpu_key.set_option(k, v)
             outs[cfg] = gpu_key.pbs(cts, lut[None], idx)
@@ -629,8 +629,8 @@ def test_throughput_blind_rotation_layouts_bit_identical(client_key, gpu_key, fc
             gpu_key.set_option(k, v)
         gpu_key.set_latency_threshold(prev_lat)
     for cfg, out in outs.items():
-        ref = outs[(cfg[0], 4, 1, 0, 0, 0, 1)]
+        ref = outs[(cfg[0], 4, 1, 0, 0, 0, 1, 0)]
         assert (out == ref).all(), cfg
-    out = outs[(1, 6, 1, 0, 0, 0, 1)]
+    out = outs[(1, 6, 1, 0, 0, 0, 1, 8)]
     for i in (0, 1, 63, 64, 591, 592, 887, 888, n - 1):
         assert fck.decrypt_block(out[i]) == f(int(msgs[i % 64]))

@@ -27,6 +27,7 @@ def main():
         rc = L.fb_pbs_batch(sk._h, p(h_in), p(lut), n_luts, p(idx), B, p(h_out)); assert rc == 0
     sk.timing(True)
     sk.set_option("br_sync", int(os.environ.get("PROBE_SYNC", "1")))
+    sk.set_option("br_resync", int(os.environ.get("PROBE_RESYNC", "8")))
     for chunks in (3,):
         sk.set_option("pbs_chunks", chunks)
         call(); call()
